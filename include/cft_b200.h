@@ -1,0 +1,147 @@
+/*
+ * cft_b200.h -- C ABI of the B200-native two-stream CFT (yolov5-CFTx3) forward path.
+ *
+ * Every entry point takes raw DEVICE pointers, explicit shapes/strides and a CUDA stream
+ * (passed as void*, i.e. a cudaStream_t / CUstream handle; NULL = legacy default stream).
+ * No torch types, no C++ exceptions, no allocation inside: the caller owns every buffer.
+ * Return value: 0 = ok, otherwise a CFT_E_* code; cft_last_error() gives the text.
+ *
+ * Activations are NHWC ("channels last") bf16.  A tensor argument is described by
+ *   (ptr, ld, coff): element (b,y,x,c) lives at ptr[((b*H + y)*W + x)*ld + coff + c]
+ * so a producer can write straight into a channel slice of its consumer's buffer
+ * (that is how Concat is fused away).
+ *
+ * The reference has no native code; each function below names the
+ * reference Python it replaces (paths relative to the reference root).
+ */
+#ifndef CFT_B200_H
+#define CFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFT_ABI_VERSION 1
+
+enum {
+  CFT_OK = 0,
+  CFT_E_ARG = 1,        /* bad argument (shape, alignment, null pointer)            */
+  CFT_E_CUDA = 2,       /* CUDA runtime / driver error (text in cft_last_error())   */
+  CFT_E_UNSUPPORTED = 3 /* valid request this build does not implement              */
+};
+
+enum { CFT_ACT_NONE = 0, CFT_ACT_SILU = 1, CFT_ACT_GELU = 2 };
+enum { CFT_DT_BF16 = 0, CFT_DT_F32 = 1 };
+
+/* kernel ids for the profiling counters */
+enum {
+  CFT_K_CONV_TCGEN05 = 0, CFT_K_CONV_REF = 1, CFT_K_FOCUS = 2, CFT_K_MAXPOOL = 3,
+  CFT_K_UPSAMPLE = 4, CFT_K_ADD = 5, CFT_K_COPY = 6, CFT_K_POOL_TOKENS = 7,
+  CFT_K_LAYERNORM = 8, CFT_K_ATTENTION = 9, CFT_K_UNPOOL = 10, CFT_K_DETECT = 11,
+  CFT_K_COUNT = 12
+};
+
+int cft_abi_version(void);
+const char* cft_last_error(void);
+/* Fails (CFT_E_UNSUPPORTED) unless the current device is compute capability 10.x. */
+int cft_check_device(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused convolution / GEMM:  y = act(conv(x, w) + bias) [+ res]
+ *   Replaces Conv.forward / Conv.fuseforward (models/common.py:36-50) with BN folded
+ *   (utils/torch_utils.py:181-201), the 1x1/3x3 convs inside Bottleneck (:99-109),
+ *   C3 (:131-143), SPP (:154-165), Focus (:168-180), the Detect 1x1 convs
+ *   (models/yolo_test.py:46) and, with k=1,B=1,H=1,W=M, every nn.Linear of
+ *   SelfAttention / myTransformerBlock (models/common.py:450-453,533-536).
+ *
+ *   x   : bf16 NHWC [B,H,W,ldx], channels [x_coff, x_coff+Cin)
+ *   w   : bf16 packed [Cout][k*k][Cin_p] (Cin_p = Cin rounded up to 8; tap = ky*k+kx)
+ *   bias: f32 [Cout] or NULL
+ *   k in {1,3}; stride in {1,2}; pad = k/2; Ho = ceil(H/stride), Wo = ceil(W/stride)
+ *   res : optional residual, added AFTER the activation; dtype = out_dtype
+ *   y   : [B,Ho,Wo,ldy] channels [y_coff, y_coff+Cout), bf16 or f32
+ * ------------------------------------------------------------------------------------- */
+typedef struct cft_conv_args {
+  const void* x; int B, H, W, Cin, ldx, x_coff;
+  const void* w; const float* bias; int Cout, k, stride, act;
+  const void* res; int ldr, r_coff;
+  void* y; int ldy, y_coff, out_dtype;
+} cft_conv_args;
+
+/* tcgen05 / TMA / TMEM implicit-GEMM kernel (the product path). */
+int cft_conv2d(const cft_conv_args* a, void* stream);
+/* Plain CUDA-core restatement of the same contract; slow; used by the GPU tests to
+ * cross-check the tcgen05 kernel.  Never called by the forward path. */
+int cft_conv2d_ref(const cft_conv_args* a, void* stream);
+
+/* Focus space-to-depth gather (models/common.py:179): NCHW image [B,3,H,W] (f32 or bf16,
+ * in_dtype = CFT_DT_*) -> NHWC bf16 [B,H/2,W/2,16]; channel = (dy + 2*dx)*3 + c, 12..15 = 0. */
+int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, void* y, void* stream);
+
+/* MaxPool k x k, stride 1, pad k/2 (-inf padding) on an NHWC bf16 channel slice
+ * (SPP, models/common.py:160-165).  src/dst may be slices of the same buffer. */
+int cft_maxpool_s1(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff,
+                   int B, int H, int W, int C, int k, void* stream);
+
+/* nn.Upsample(None, 2, 'nearest') (yaml rows 33/37): [B,H,W,C] -> [B,2H,2W,C]. */
+int cft_upsample2x(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff,
+                   int B, int H, int W, int C, void* stream);
+
+/* Add / Add2 (models/common.py:222-243): y = a + b on bf16 channel slices, npix = B*H*W. */
+int cft_add(const void* a, int lda, int a_coff, const void* b, int ldb, int b_coff,
+            void* y, int ldy, int y_coff, long long npix, int C, void* stream);
+
+/* Concat fallback (models/common.py:219): copy a channel slice. */
+int cft_copy(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff,
+             long long npix, int C, void* stream);
+
+/* GPT front end (models/common.py:608-621): AdaptiveAvgPool2d((va,ha)) of both modalities,
+ * tokenise (RGB tokens first, token = row*ha+col), + pos_emb.  Output f32 [B, 2*va*ha, C]. */
+int cft_gpt_pool_tokens(const void* rgb, int ld_rgb, int coff_rgb,
+                        const void* ir, int ld_ir, int coff_ir,
+                        int B, int H, int W, int C, int va, int ha,
+                        const float* pos_emb, float* tokens, void* stream);
+
+/* LayerNorm over the last dim (models/common.py:529-530,572), f32 in, eps explicit.
+ * out_dtype selects bf16 (GEMM operand) or f32 output. */
+int cft_layernorm(const float* x, const float* gamma, const float* beta, float eps,
+                  long long rows, int C, void* y, int out_dtype, void* stream);
+
+/* Multi-head self-attention core (models/common.py:497-510): qkv bf16 [B*T, 3*C] holding
+ * q|k|v (head h at columns h*dk of each third), T tokens per image (T <= 128),
+ * out bf16 [B*T, C] = softmax(q k^T / sqrt(dk)) v with heads merged. */
+int cft_attention(const void* qkv, void* out, int B, int T, int C, int heads, void* stream);
+
+/* GPT back end (models/common.py:626-637) fused with Add2 (:239-242) and Add (:229):
+ * tok f32 [B, 2*va*ha, C] (after ln_f) is bilinearly upsampled (align_corners=False) to HxW
+ * per modality; out_rgb = x_rgb + up_rgb, out_ir = x_ir + up_ir, out_sum = out_rgb + out_ir.
+ * x_rgb/x_ir NULL -> the upsampled map alone is written (plain GPT.forward output).
+ * out_sum may be NULL.  All maps NHWC bf16 with (ld, coff). */
+int cft_gpt_unpool(const float* tok, int B, int H, int W, int C, int va, int ha,
+                   const void* x_rgb, int ld_xr, int coff_xr,
+                   const void* x_ir, int ld_xi, int coff_xi,
+                   void* out_rgb, int ld_or, int coff_or,
+                   void* out_ir, int ld_oi, int coff_oi,
+                   void* out_sum, int ld_os, int coff_os, void* stream);
+
+/* Detect tail (models/yolo_test.py:48-59) for one level: head f32 [B*ny*nx, ldh] holding
+ * na*no conv outputs per pixel (channel = a*no + o) ->
+ *   raw f32 [B,na,ny,nx,no]   (the permuted head, :48)
+ *   z   f32 [B, z_rows, no] rows [z_row0 + a*ny*nx + j*nx + i]  (sigmoid + grid/anchor decode)
+ * anchors_px: na*2 floats (anchor_grid of this level, pixels). */
+int cft_detect_decode(const float* head, int ldh, int B, int ny, int nx, int na, int no,
+                      float stride, const float* anchors_px,
+                      float* raw, float* z, long long z_rows, long long z_row0, void* stream);
+
+/* ---- profiling counters (CUDA events around every launch while enabled) ---- */
+int cft_prof_enable(int on);            /* resets counters when turned on           */
+int cft_prof_get(int kernel_id, double* total_ms, long long* launches);
+long long cft_launch_count(void);       /* kernels launched by this library so far  */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFT_B200_H */

@@ -1,0 +1,63 @@
+// Shared host/device helpers of libcft_b200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cft_b200.h"
+
+namespace cft {
+
+// ---------------------------------------------------------------- host-side bookkeeping
+void set_error(const char* fmt, ...);
+int fail_arg(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// Wraps one kernel launch: launch counter + optional CUDA-event profiling per kernel id.
+struct LaunchScope {
+  int id;
+  cudaStream_t stream;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  LaunchScope(int kernel_id, cudaStream_t s);
+  int finish(const char* what);  // call right after the <<<>>>; returns CFT_* code
+};
+
+int sm_count();
+
+#define CFT_REQUIRE(cond, ...)                      \
+  do {                                              \
+    if (!(cond)) return ::cft::fail_arg(__VA_ARGS__); \
+  } while (0)
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CFT_ACT_SILU) return silu_f(v);
+  if (act == CFT_ACT_GELU) return gelu_f(v);
+  return v;
+}
+
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+}  // namespace cft

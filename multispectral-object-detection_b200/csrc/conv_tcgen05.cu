@@ -1,0 +1,536 @@
+// Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (sm_100a):
+//   D[128 pixels, block_n couts] (fp32, TMEM) += A[128 pixels, 64 cin] * W[block_n couts, 64 cin]^T
+//
+//  * A tiles come straight from the NHWC activation tensor through a 4-D TMA tensor map
+//    (C, W, H, B) with box (64, TW, TH, 1): one box per filter tap, shifted by the tap's
+//    (dx, dy); out-of-bounds rows/cols/channels are zero-filled by TMA == conv zero padding
+//    and K-tail padding.  Stride-2 convs use four "parity" maps (base pointer offset by
+//    (py, px), W/H strides doubled) so every tap is again a dense box.
+//    1x1 convs and nn.Linear are the same kernel with taps = 1, H = B = 1, W = M.
+//  * W tiles come from a 3-D map (Cin, taps, Cout) over the packed [Cout][taps][Cin_p] weights.
+//  * 128B-swizzled K-major smem tiles feed tcgen05.mma (UMMA 128 x block_n x 16, bf16 -> fp32),
+//    accumulators live in TMEM (2 x 256 columns, double buffered across tiles).
+//  * Warp roles (256 threads, persistent CTAs, static round-robin tile schedule):
+//      warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM alloc | warps 4-7 epilogue
+//    Epilogue: tcgen05.ld -> +bias -> SiLU/GELU -> +residual -> bf16/f32 -> global (NHWC slice).
+//
+// Replaces the cuDNN/cuBLAS calls the reference reaches through nn.Conv2d / nn.Linear
+// (models/common.py:41-50,450-453,533-536; models/yolo_test.py:46).
+#include "cft_common.cuh"
+
+namespace {
+
+using namespace cft;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // bf16 elements = one 128B swizzle row
+constexpr int kThreads = 256;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
+constexpr int kTmemCols = 512;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct __align__(64) TensorMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct ConvParams {
+  int B, Ho, Wo, Cout;
+  int taps, kchunks, stride;
+  int TW, TH, tiles_x, tiles_y;
+  int n_blocks, block_n, num_tiles, stages;
+  int act, out_f32;
+  int ldy, y_coff, ldr, r_coff;
+  const float* bias;
+  void* y;
+  const void* res;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin == 64) t0 = clock64();
+    if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("cft conv_tcgen05: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);   // start address        bits [0,14)
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;          // stride byte offset   bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                   // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                   // layout SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TileCoord {
+  int b, y0, x0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  const int nb = tile % p.n_blocks;
+  int m = tile / p.n_blocks;
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  t.b = m / p.tiles_y;
+  t.y0 = ty * p.TH;
+  t.x0 = tx * p.TW;
+  t.n0 = nb * p.block_n;
+  return t;
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const uint32_t b_tile_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * kATileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + stages * b_tile_bytes);
+  uint64_t* full_bar = bars;                   // [kMaxStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kMaxStages;     // [kMaxStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2; // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_iters = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH) * 128u + b_tile_bytes;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int tap = 0; tap < p.taps; ++tap) {
+        int mi = 0, dy = 0, dx = 0;
+        if (p.taps == 9) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          if (p.stride == 1) {
+            dy = ky - 1;
+            dx = kx - 1;
+          } else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
+            const int py = (ky != 1), px = (kx != 1);
+            dy = (ky == 0) ? -1 : 0;
+            dx = (kx == 0) ? -1 : 0;
+            mi = py * 2 + px;
+          }
+        }
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * kBlockK, t.x0 + dx,
+                        t.y0 + dy, t.b);
+            tma_load_3d(smem_b + stage * b_tile_bytes, &maps.b, &full_bar[stage], kc * kBlockK, tap, t.n0);
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = umma_idesc(static_cast<uint32_t>(p.block_n));
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * b_tile_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);               // smem slot free once these MMAs retire
+          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;     // accumulator row = pixel within the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ty_in = row / p.TW, tx_in = row - ty_in * p.TW;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int oy = t.y0 + ty_in, ox = t.x0 + tx_in;
+      const bool valid = (ty_in < p.TH) && (oy < p.Ho) && (ox < p.Wo);
+      const size_t pix = (static_cast<size_t>(t.b) * p.Ho + oy) * p.Wo + ox;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int col = c0 + j;
+            const int n = t.n0 + col;
+            if (col < p.block_n && n < p.Cout) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.act != CFT_ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+              }
+              if (p.out_f32) {
+                float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + n;
+                if (p.res) {
+                  const float* rp = reinterpret_cast<const float*>(p.res) + pix * p.ldr + p.r_coff + n;
+                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                }
+                *reinterpret_cast<float4*>(yp) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(yp + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + n;
+                if (p.res) {
+                  const __nv_bfloat16* rp =
+                      reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.ldr + p.r_coff + n;
+                  float r[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(rp), r);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += r[i];
+                }
+                *reinterpret_cast<bf16x8*>(yp) = pack8(f);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+               const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return CFT_E_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], box[2], rank > 3 ? box[3] : 0);
+    return CFT_E_CUDA;
+  }
+  return CFT_OK;
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Largest multiple of 16 (<= 256) that divides Cout with the fewest blocks; falls back to 256 + tail.
+int pick_block_n(int cout) {
+  if (cout <= 256) return round_up(cout, 16);
+  int nb = (cout + 255) / 256;
+  for (;; ++nb) {
+    if (nb > cout / 16) break;
+    if (cout % nb == 0 && (cout / nb) % 16 == 0 && cout / nb <= 256) return cout / nb;
+    if (nb > 64) break;
+  }
+  return 256;
+}
+
+void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
+  long best = -1;
+  int bw = 1, bh = 1;
+  for (int tw = 1; tw <= 128 && tw <= Wo; ++tw) {
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th < 1) continue;
+    const long tiles = static_cast<long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    // fewest tiles first, then the widest rows (longer contiguous runs per TMA box row)
+    const long score = tiles * 1024 - tw;
+    if (best < 0 || score < best) {
+      best = score;
+      bw = tw;
+      bh = th;
+    }
+  }
+  *TW = bw;
+  *TH = bh;
+}
+
+bool g_attr_set = false;
+
+}  // namespace
+
+extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  CFT_REQUIRE(a && a->x && a->w && a->y, "cft_conv2d: null pointer");
+  CFT_REQUIRE(a->k == 1 || a->k == 3, "cft_conv2d: k must be 1 or 3 (got %d)", a->k);
+  CFT_REQUIRE(a->stride == 1 || (a->stride == 2 && a->k == 3), "cft_conv2d: stride %d with k %d unsupported",
+              a->stride, a->k);
+  CFT_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "cft_conv2d: empty shape");
+  CFT_REQUIRE(a->Cin % 8 == 0 && a->ldx % 8 == 0 && a->x_coff % 8 == 0,
+              "cft_conv2d: Cin/ldx/x_coff must be multiples of 8 (got %d/%d/%d)", a->Cin, a->ldx, a->x_coff);
+  CFT_REQUIRE(a->Cout % 8 == 0 && a->ldy % 8 == 0 && a->y_coff % 8 == 0,
+              "cft_conv2d: Cout/ldy/y_coff must be multiples of 8 (got %d/%d/%d)", a->Cout, a->ldy, a->y_coff);
+  CFT_REQUIRE(!a->res || (a->ldr % 8 == 0 && a->r_coff % 8 == 0), "cft_conv2d: residual ld/coff must be multiples of 8");
+  CFT_REQUIRE(a->x_coff + a->Cin <= a->ldx && a->y_coff + a->Cout <= a->ldy, "cft_conv2d: channel slice out of range");
+  CFT_REQUIRE(reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->w) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(a->y) % 16 == 0,
+              "cft_conv2d: pointers must be 16-byte aligned");
+  CFT_REQUIRE(a->stride == 1 || (a->H % 2 == 0 && a->W % 2 == 0), "cft_conv2d: stride 2 needs even H, W");
+  CFT_REQUIRE(a->out_dtype == CFT_DT_BF16 || a->out_dtype == CFT_DT_F32, "cft_conv2d: bad out_dtype");
+
+  const int s = a->stride;
+  ConvParams p;
+  p.B = a->B;
+  p.Ho = (a->H + s - 1) / s;
+  p.Wo = (a->W + s - 1) / s;
+  p.Cout = a->Cout;
+  p.taps = a->k * a->k;
+  p.kchunks = (a->Cin + kBlockK - 1) / kBlockK;
+  p.stride = s;
+  pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
+  p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
+  p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
+  p.block_n = pick_block_n(a->Cout);
+  p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
+  const long long tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y * p.n_blocks;
+  CFT_REQUIRE(tiles < (1LL << 31), "cft_conv2d: too many tiles");
+  p.num_tiles = static_cast<int>(tiles);
+  const int stage_bytes = kATileBytes + p.block_n * 128;
+  p.stages = kSmemBudget / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.act = a->act;
+  p.out_f32 = a->out_dtype == CFT_DT_F32;
+  p.ldy = a->ldy;
+  p.y_coff = a->y_coff;
+  p.ldr = a->ldr;
+  p.r_coff = a->r_coff;
+  p.bias = a->bias;
+  p.y = a->y;
+  p.res = a->res;
+
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a->x) + a->x_coff;
+  const cuuint64_t eb = 2;
+  int rc;
+  if (s == 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
+    cuuint64_t str[3] = {(cuuint64_t)a->ldx * eb, (cuuint64_t)a->W * a->ldx * eb,
+                         (cuuint64_t)a->H * a->W * a->ldx * eb};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    rc = encode_map(&maps.a[0], xb, 4, dims, str, box);
+    if (rc) return rc;
+    maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)(a->W / 2), (cuuint64_t)(a->H / 2), (cuuint64_t)a->B};
+        cuuint64_t str[3] = {(cuuint64_t)2 * a->ldx * eb, (cuuint64_t)2 * a->W * a->ldx * eb,
+                             (cuuint64_t)a->H * a->W * a->ldx * eb};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        const __nv_bfloat16* base = xb + (static_cast<size_t>(py) * a->W + px) * a->ldx;
+        rc = encode_map(&maps.a[py * 2 + px], base, 4, dims, str, box);
+        if (rc) return rc;
+      }
+  }
+  {
+    const int cin_p = round_up(a->Cin, 8);
+    cuuint64_t dims[3] = {(cuuint64_t)a->Cin, (cuuint64_t)p.taps, (cuuint64_t)a->Cout};
+    cuuint64_t str[2] = {(cuuint64_t)cin_p * eb, (cuuint64_t)p.taps * cin_p * eb};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)p.block_n};
+    rc = encode_map(&maps.b, a->w, 3, dims, str, box);
+    if (rc) return rc;
+  }
+
+  const int smem_bytes = 1024 + p.stages * stage_bytes + 256;
+  if (!g_attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         1024 + kSmemBudget + 256),
+                    "cudaFuncSetAttribute(conv_tcgen05)");
+    if (rc) return rc;
+    g_attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  LaunchScope ls(CFT_K_CONV_TCGEN05, stream);
+  cft_conv_tcgen05_kernel<<<grid, kThreads, smem_bytes, stream>>>(maps, p);
+  return ls.finish("cft_conv2d launch");
+}

@@ -67,7 +67,7 @@ def main():
             "input_checksum": [checksum(x), checksum(x2)],
             "state_checksum": state_checksum(sd),
             "oracle_vs_reference_max_abs": [dz, dr],
-            "torch": torch.__version__,
+            "torch": str(torch.__version__),
         }, os.path.join(out_dir, name + ".pt"))
         print(f"{name}: z{tuple(z_ref.shape)} oracle-vs-reference max|d| z={dz:.2e} raw={dr:.2e}")
 

@@ -1,0 +1,115 @@
+"""CPU suite: host-side logic -- graph configs, module/state_dict mirror, planner, C-ABI exports,
+drop-in install/convert into the reference namespace, and "fails loudly without CUDA"."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import yaml
+
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", ["yolov5l_fusion_transformerx3_FLIR_aligned", "yolov5l_fusion_transformerx3_llvip",
+                                  "yolov5s_fusion_transformerx3_vedai"])
+def test_generated_config_equals_reference_yaml(name, cft):
+    with open(ref_shim.reference_yaml(name)) as f:
+        assert yaml.safe_load(f) == cft.named_config(name)
+
+
+@pytest.mark.parametrize("name,nkeys,nparams", [
+    ("yolov5s_fusion_transformerx3_vedai", 965, 44.54e6),
+    ("yolov5l_fusion_transformerx3_FLIR_aligned", 1445, 206.26e6),
+    ("yolov5x_fusion_transformerx3_FLIR_aligned", 1685, 344.52e6),
+])
+def test_model_state_dict_mirrors_reference(name, nkeys, nparams, cft, oracle):
+    cfg = cft.named_config(name)
+    model = cft.Model(cfg)
+    sd = oracle.init_state(cfg)                      # reference key names (pinned by make_golden.py)
+    msd = model.state_dict()
+    assert len(msd) == nkeys and set(msd) == set(sd)
+    assert all(msd[k].shape == sd[k].shape for k in sd)
+    model.load_state_dict(sd, strict=True)
+    n = sum(p.numel() for p in model.parameters())
+    assert abs(n - nparams) / nparams < 1e-3
+    assert [m.i for m in model.model] == list(range(47))
+    det = model.model[-1]
+    assert det.stride.tolist() == [8.0, 16.0, 32.0] and det.no == cfg["nc"] + 5
+    assert torch.allclose(det.anchors * det.stride.view(-1, 1, 1), det.anchor_grid.view(3, 3, 2))
+
+
+def test_planner_finds_concat_slots_and_gpt_groups(cft):
+    model = cft.Model(cft.named_config("yolov5l_fusion_transformerx3_FLIR_aligned"))
+    plan = model._plan
+    assert plan["gpt_groups"] == {10: {"rgb": 11, "ir": 12, "sum": 29}, 17: {"rgb": 18, "ir": 19, "sum": 30},
+                                  26: {"rgb": 27, "ir": 28, "sum": 31}}
+    assert plan["slots"][33][:4] == (34, 0, 512, 1024) and plan["slots"][30][:4] == (34, 512, 1024, 1024)
+    assert plan["slots"][32][:4] == (44, 512, 1024, 1024) and plan["slots"][36][:4] == (41, 256, 512, 512)
+    assert sorted(set(model.save)) == [1, 4, 9, 10, 11, 12, 14, 16, 17, 18, 19, 22, 25, 26, 27, 28, 29, 30, 32, 36, 39, 42, 45]
+
+
+def test_c_abi_exports_every_declared_symbol(cft):
+    header = open(os.path.join(ROOT, "include", "cft_b200.h")).read()
+    declared = set(re.findall(r"\b(cft_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = cft.load()                                   # dlopen only; no device work
+    for name in declared:
+        assert hasattr(lib, name), f"libcft_b200.so does not export {name}"
+    assert set(cft._lib.SIGNATURES) == declared
+    assert lib.cft_abi_version() == 1
+
+
+def test_forward_fails_loudly_without_cuda(cft):
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    model = cft.Model(cft.named_config("yolov5s_fusion_transformerx3_vedai")).eval()
+    x = torch.rand(1, 3, 64, 64)
+    with pytest.raises(cft.CftError):
+        model(x, x)
+
+
+def test_weight_packing_folds_bn_like_reference(cft):
+    """pack_conv_weight == fuse_conv_and_bn (utils/torch_utils.py:181-201) then OIHW -> [O][tap][I]."""
+    from importlib import import_module
+    model_mod = import_module("multispectral-object-detection_b200.model")
+    torch.manual_seed(0)
+    conv = cft.Conv(16, 24, 3, 1)
+    conv.bn.eps = 1e-3
+    conv.bn.weight.data.uniform_(0.5, 1.5); conv.bn.bias.data.normal_(0, .1)
+    conv.bn.running_mean.normal_(0, .1); conv.bn.running_var.uniform_(.5, 1.5)
+    fused = model_mod.fuse_conv_and_bn(conv.conv, conv.bn)
+    w, b = cft.ops.pack_conv_weight(conv.conv.weight, None, (conv.bn.weight, conv.bn.bias, conv.bn.running_mean,
+                                                              conv.bn.running_var, conv.bn.eps))
+    ref = fused.weight.detach().permute(0, 2, 3, 1).reshape(24, 9, 16)
+    assert w.shape == (24, 9, 16) and w.dtype == torch.bfloat16
+    assert (w.float() - ref).abs().max() <= ref.abs().max() * 2 ** -8
+    assert torch.allclose(b, fused.bias.detach(), atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present (GPU box)")
+def test_install_and_convert_into_reference(cft, oracle):
+    yt = ref_shim.import_reference()
+    name = "yolov5s_fusion_transformerx3_vedai"
+    cfg = cft.named_config(name)
+    sd = oracle.init_state(cfg)
+    prev = cft.install(yt)
+    try:
+        rm = yt.Model(ref_shim.reference_yaml(name), ch=3).eval()      # the reference's own Model/parse_model
+    finally:
+        cft.uninstall(yt, prev)
+    mods = {type(m).__module__ for m in rm.model}
+    assert mods == {"multispectral-object-detection_b200.modules"}
+    rm.load_state_dict(sd, strict=True)
+    assert sorted(set(rm.save)) == sorted(set(cft.Model(cfg).save))
+    # convert(): an already-built reference model keeps its weights
+    rm2 = yt.Model(ref_shim.reference_yaml(name), ch=3).eval()
+    assert type(rm2.model[0]).__module__ == "models.common"
+    rm2.load_state_dict(sd, strict=True)
+    rm3 = cft.convert(rm2)
+    sd3 = rm3.state_dict()
+    assert set(sd3) == set(sd) and all(torch.equal(sd3[k], sd[k]) for k in sd)
+    assert all(type(m).__module__ == "multispectral-object-detection_b200.modules" for m in rm3.model)
