@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- RGB+IR pairs/s of the yolov5l-CFTx3 two-stream forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 32] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward of the hot path over one batch of synthetic 640x640 RGB+IR pairs
+(config 2 of BASELINE.json: yolov5l_fusion_transformerx3 FLIR cfg, bf16, batch 32 per GPU).
+Prints ONE JSON line on rank 0:
+  value      whole-job pairs/s, inputs resident in HBM, K steps timed with CUDA events between
+             barrier+synchronize on both sides, max over ranks (weak scaling: batch 32 per GPU)
+  e2e        the same metric through the public API from HOST buffers: every step copies the loader's
+             uint8 [B,6,H,W] wire-format batch from pinned host memory to the device and reads the decoded
+             detections z back to the host, all inside the timed region
+  roofline   the dominant kernel (tcgen05 implicit-GEMM conv/linear): algorithmic conv+linear FLOPs per
+             step / time spent in that kernel per step (CUDA events around every launch, measured live in a
+             separate profiled pass), against the measured sustained bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (a port of the reference's PyTorch forward) timed on the host cores on a
+             bounded sample (batch-1 forwards of the same graph/size)
+--impl reference: the reference's own CPU implementation of the path (the oracle port; the reference is
+pure Python and /root/reference does not exist on the GPU box) on all host threads, rank 0 only.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RGB+IR pairs/sec yolov5l-CFTx3 fwd @640"
+CFG_NAME = "yolov5l_fusion_transformerx3_FLIR_aligned"
+H = W = 640
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(seconds_budget=20.0, batch=1):
+    """The oracle port of the reference forward on the host cores: batch-1 forwards of the headline graph."""
+    import torch
+    from oracle import cft_oracle as O
+    pkg = importlib.import_module("multispectral-object-detection_b200")
+    cfg = pkg.named_config(CFG_NAME)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state(cfg, seed=0)
+    x, x2 = O.make_inputs(batch, H, W, seed=1)
+    O.forward(sd, cfg, x, x2)                       # warm-up
+    times, t_start = [], time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < 50):
+        t0 = time.perf_counter()
+        O.forward(sd, cfg, x, x2)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": batch / med, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} forwards of batch {batch} @ {H}x{W} (fp32 oracle, median {med * 1e3:.0f} ms)"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch
+    from oracle import cft_oracle as O
+    pkg = importlib.import_module("multispectral-object-detection_b200")
+    cfg = pkg.named_config(CFG_NAME)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state(cfg, seed=0)
+    b = 1                                             # bounded sample per step
+    x, x2 = O.make_inputs(b, H, W, seed=1)
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.forward(sd, cfg, x, x2)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.forward(sd, cfg, x, x2)
+    dt = time.perf_counter() - t0
+    v = b * steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{CFG_NAME} forward, {H}x{W}, CPU oracle port of the reference forward, "
+                                   f"bounded sample: batch {b} per step"},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} forwards of batch {b} @ {H}x{W}"},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (weak scaling)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("multispectral-object-detection_b200")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(args.warmup, 3)
+    K = args.steps
+    B = args.batch
+
+    cfg = pkg.named_config(CFG_NAME)
+    torch.manual_seed(0)
+    model = pkg.Model(cfg).eval()
+    # random-init weights of the architecture with non-degenerate BN statistics / pos_emb
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+            if isinstance(m, pkg.GPT):
+                m.pos_emb.copy_(torch.randn(m.pos_emb.shape, generator=g) * 0.02)
+    model = model.to(dev)
+
+    gi = torch.Generator().manual_seed(1 + rank)
+    x6_host = torch.randint(0, 256, (B, 6, H, W), dtype=torch.uint8, generator=gi).pin_memory()
+    x6 = x6_host.to(dev)                       # inputs resident in HBM for the `value` measurement
+    x_rgb, x_ir = x6[:, :3], x6[:, 3:]
+
+    def step():
+        return model(x_rgb, x_ir)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up (also builds packed weights) ----------------
+    with torch.no_grad():
+        for _ in range(W_):
+            z, _ = step()
+    torch.cuda.synchronize()
+
+    # ---------------- optional CUDA graph of the whole forward ----------------
+    graph, launches_per_step = None, None
+    n0 = pkg._lib.launch_count()
+    with torch.no_grad():
+        step()
+    launches_per_step = pkg._lib.launch_count() - n0
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                z_g, _ = step()
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+            z = z_g
+        except Exception as e:              # noqa: BLE001  -- eager launches remain a valid (slower) path
+            print(f"[bench] CUDA graph capture failed, timing eager launches: {e}", file=sys.stderr)
+            graph = None
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    # ---------------- timed region: K steps, device-resident inputs ----------------
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0.record()
+        for _ in range(K):
+            run_step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max / 1e3)
+
+    # ---------------- end-to-end: host uint8 batch -> device -> forward -> z back to host ----------------
+    z_host = torch.empty(z.shape, dtype=z.dtype).pin_memory()
+    x6_e2e = torch.empty_like(x6)
+
+    def e2e_step():
+        x6_e2e.copy_(x6_host, non_blocking=True)
+        zz, _ = model(x6_e2e[:, :3], x6_e2e[:, 3:])
+        z_host.copy_(zz, non_blocking=True)
+
+    with torch.no_grad():
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(t.item()) / 1e3)
+    h2d = x6_host.numel() * x6_host.element_size()
+    d2h = z_host.numel() * z_host.element_size()
+
+    # ---------------- roofline of the dominant kernel (profiled eager pass, rank 0) ----------------
+    roofline, kernel_ms = None, None
+    if rank == 0:
+        from oracle import cft_oracle as O       # FLOP model only -- nothing is executed
+        peaks = load_peaks()
+        flops_pair = O.conv_linear_flops(cfg, H, W)
+        attn_core = sum(8 * 4.0 * 128 * 128 * d for d in (256, 512, 1024))
+        pkg._lib.prof_enable(True)
+        nprof = 3
+        with torch.no_grad():
+            for _ in range(nprof):
+                step()
+        torch.cuda.synchronize()
+        prof = pkg._lib.prof_get()
+        pkg._lib.prof_enable(False)
+        kernel_ms = {k: round(v[0] / nprof, 4) for k, v in prof.items() if v[1]}
+        conv_ms, conv_n = prof["conv_tcgen05"]
+        conv_flops_step = (flops_pair - attn_core) * B
+        achieved = conv_flops_step * nprof / (conv_ms / 1e3) / 1e12
+        roofline = {"kernel": "cft_conv_tcgen05_kernel", "bound": "tensor", "achieved": achieved,
+                    "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                    "peak_source": peaks["source"] + " sustained bf16", "traffic": None,
+                    "launches_per_step": conv_n // nprof, "ms_per_step_in_kernel": conv_ms / nprof,
+                    "algorithmic_gflop_per_step": conv_flops_step / 1e9,
+                    "whole_forward_tensor_frac": (flops_pair * value / world) / (peaks["tflops_sustained"] * 1e12)}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_baseline()
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{CFG_NAME} forward (eval, BN folded), batch {B} per GPU @ {H}x{W}, nc=3",
+                       "global_batch": B * world, "parallelism": f"dp{world} (pairs sharded, no data-path collective)",
+                       "l2": "working set (inputs 79 MB + weights 412 MB + activations > 5 GB per step) >> 126 MB L2",
+                       "launch": "cuda-graph replay" if graph is not None else "eager"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * K,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,7 +34,7 @@ enum {
 };
 
 enum { CFT_ACT_NONE = 0, CFT_ACT_SILU = 1, CFT_ACT_GELU = 2 };
-enum { CFT_DT_BF16 = 0, CFT_DT_F32 = 1 };
+enum { CFT_DT_BF16 = 0, CFT_DT_F32 = 1, CFT_DT_U8 = 2 };
 
 /* kernel ids for the profiling counters */
 enum {
@@ -77,9 +77,14 @@ int cft_conv2d(const cft_conv_args* a, void* stream);
  * cross-check the tcgen05 kernel.  Never called by the forward path. */
 int cft_conv2d_ref(const cft_conv_args* a, void* stream);
 
-/* Focus space-to-depth gather (models/common.py:179): NCHW image [B,3,H,W] (f32 or bf16,
- * in_dtype = CFT_DT_*) -> NHWC bf16 [B,H/2,W/2,16]; channel = (dy + 2*dx)*3 + c, 12..15 = 0. */
-int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, void* y, void* stream);
+/* Focus space-to-depth gather (models/common.py:179): NCHW image [B,3,H,W] -> NHWC bf16
+ * [B,H/2,W/2,16]; channel = (dy + 2*dx)*3 + c, 12..15 = 0.  in_dtype: CFT_DT_F32 / CFT_DT_BF16
+ * (values already in [0,1]) or CFT_DT_U8 -- the data loader's wire format (utils/datasets.py:1272-1281),
+ * scaled by 1/255 here as train.py:715 / test.py:107-108 do on the device.  batch_stride = elements
+ * between consecutive images (3*H*W for a dense tensor; 6*H*W when RGB / IR are the two halves of the
+ * loader's [B,6,H,W] tensor, train.py:716-717). */
+int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long long batch_stride,
+                     void* y, void* stream);
 
 /* MaxPool k x k, stride 1, pad k/2 (-inf padding) on an NHWC bf16 channel slice
  * (SPP, models/common.py:160-165).  src/dst may be slices of the same buffer. */

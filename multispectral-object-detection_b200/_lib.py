@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcft_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
-DT_BF16, DT_F32 = 0, 1
+DT_BF16, DT_F32, DT_U8 = 0, 1, 2
 KERNEL_IDS = {
     "conv_tcgen05": 0, "conv_ref": 1, "focus": 2, "maxpool": 3, "upsample": 4, "add": 5, "copy": 6,
     "pool_tokens": 7, "layernorm": 8, "attention": 9, "unpool": 10, "detect": 11,
@@ -41,7 +41,7 @@ SIGNATURES = {
     "cft_check_device": ([C.POINTER(_I)] * 3, _I),
     "cft_conv2d": ([C.POINTER(ConvArgs), _P], _I),
     "cft_conv2d_ref": ([C.POINTER(ConvArgs), _P], _I),
-    "cft_focus_gather": ([_P, _I, _I, _I, _I, _P, _P], _I),
+    "cft_focus_gather": ([_P, _I, _I, _I, _I, _LL, _P, _P], _I),
     "cft_maxpool_s1": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_upsample2x": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_add": ([_P, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _I, _P], _I),

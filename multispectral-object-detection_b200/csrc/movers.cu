@@ -20,7 +20,8 @@ inline int grid_for(long long work, int threads, int max_blocks_per_sm = 16) {
 // One thread per output pixel: reads a 2x2 patch of each of the 3 planes (two float2 / bf162
 // loads per plane, consecutive threads -> consecutive addresses), writes 32 B (16 bf16).
 template <typename T>
-__global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ y, int B, int H, int W) {
+__global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                                    long long bstride) {
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -32,10 +33,14 @@ __global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __
     float f[16];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const T* p0 = img + ((static_cast<long long>(b) * 3 + c) * H + 2 * oy) * W + 2 * ox;
+      const T* p0 = img + static_cast<long long>(b) * bstride + (static_cast<long long>(c) * H + 2 * oy) * W + 2 * ox;
       const T* p1 = p0 + W;
       float a00, a01, a10, a11;
-      if constexpr (sizeof(T) == 4) {
+      if constexpr (sizeof(T) == 1) {
+        const uchar2 r0 = *reinterpret_cast<const uchar2*>(p0);
+        const uchar2 r1 = *reinterpret_cast<const uchar2*>(p1);
+        a00 = r0.x / 255.0f; a01 = r0.y / 255.0f; a10 = r1.x / 255.0f; a11 = r1.y / 255.0f;
+      } else if constexpr (sizeof(T) == 4) {
         const float2 r0 = *reinterpret_cast<const float2*>(p0);
         const float2 r1 = *reinterpret_cast<const float2*>(p1);
         a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
@@ -167,20 +172,25 @@ __global__ void conv_ref_kernel(cft_conv_args a, int Ho, int Wo, int cin_p) {
 
 using namespace cft;
 
-extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, void* y, void* stream_v) {
+extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long long batch_stride, void* y,
+                                void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   CFT_REQUIRE(img && y, "cft_focus_gather: null pointer");
   CFT_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "cft_focus_gather: H, W must be even");
   CFT_REQUIRE(reinterpret_cast<uintptr_t>(img) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0,
               "cft_focus_gather: misaligned pointer");
+  CFT_REQUIRE(batch_stride >= 3LL * H * W && batch_stride % 2 == 0, "cft_focus_gather: bad batch stride");
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2);
   LaunchScope ls(CFT_K_FOCUS, stream);
   if (in_dtype == CFT_DT_F32)
     focus_gather_kernel<float><<<grid_for(total, kThreads), kThreads, 0, stream>>>(
-        reinterpret_cast<const float*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W);
+        reinterpret_cast<const float*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, batch_stride);
   else if (in_dtype == CFT_DT_BF16)
     focus_gather_kernel<__nv_bfloat16><<<grid_for(total, kThreads), kThreads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W);
+        reinterpret_cast<const __nv_bfloat16*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, batch_stride);
+  else if (in_dtype == CFT_DT_U8)
+    focus_gather_kernel<uint8_t><<<grid_for(total, kThreads), kThreads, 0, stream>>>(
+        reinterpret_cast<const uint8_t*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, batch_stride);
   else
     return fail_arg("cft_focus_gather: bad in_dtype %d", in_dtype);
   return ls.finish("cft_focus_gather launch");

@@ -160,18 +160,23 @@ def gemm(a_mat: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act
 
 # ------------------------------------------------------------------------------ movers
 def focus_gather(img: torch.Tensor) -> torch.Tensor:
-    """NCHW image [B,3,H,W] (fp32/bf16, plain contiguous) -> NHWC bf16 [B,16,H/2,W/2] (12 used)."""
+    """NCHW image [B,3,H,W] -> NHWC bf16 [B,16,H/2,W/2] (12 used).  fp32 / bf16 values in [0,1], or uint8
+    (the loader's wire format, scaled by 1/255 in the kernel).  The batch stride may be larger than 3*H*W
+    (the RGB / IR halves of the loader's [B,6,H,W] tensor) -- no copy is made for such views."""
     lib = _lib.lib()
     _require_cuda(img, "image")
-    if img.dtype not in (torch.float32, torch.bfloat16):
+    if img.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
         img = img.float()
-    img = img.contiguous()
     b, c, h, w = img.shape
     if c != 3:
         raise _lib.CftError(f"focus_gather expects 3 input channels, got {c}")
+    if not (img.stride(3) == 1 and img.stride(2) == w and img.stride(1) == h * w and img.stride(0) % 2 == 0):
+        img = img.contiguous()
+    bstride = img.stride(0) if b > 1 else 3 * h * w
+    dt = {torch.float32: DT_F32, torch.bfloat16: DT_BF16, torch.uint8: _lib.DT_U8}[img.dtype]
     y = empty_nhwc(b, 16, h // 2, w // 2, img.device)
-    _lib.check(lib.cft_focus_gather(img.data_ptr(), DT_F32 if img.dtype == torch.float32 else DT_BF16, b, h, w,
-                                    y.data_ptr(), _stream()), "cft_focus_gather")
+    _lib.check(lib.cft_focus_gather(img.data_ptr(), dt, b, h, w, bstride, y.data_ptr(), _stream()),
+               "cft_focus_gather")
     return y
 
 

@@ -5,7 +5,7 @@ plus size-independent properties at BASELINE.json's full size (batch 32 @ 640x64
 
 Stated tolerance (bf16 activations/weights, fp32 accumulate, fp32 LN/softmax/residual stream/decode)
 against the fp32 reference, following SURVEY.md §8(c):
-  raw heads : rel-L2 <= 2e-2 and |d| <= 0.06 + 0.03*|ref| element-wise
+  raw heads : rel-L2 <= 2e-2 and |d| <= 0.05*max(1, rms(ref)) + 0.03*|ref| element-wise
   decoded z : conf/cls |d| <= 2e-2 ; xy |d| <= 0.06*stride ; wh rel <= 8e-2 (+0.5 px)
   Detect row order / grid / anchors : bit-exact on identical raw heads (test_kernels_gpu.py).
 """
@@ -35,7 +35,8 @@ def check_outputs(z, raw, z_ref, raw_ref, strides=(8, 16, 32)):
         rel_l2 = float((a - b).norm() / b.norm())
         report[f"raw{i}"] = (float(d.max()), rel_l2)
         assert rel_l2 <= 2e-2, (i, rel_l2)
-        assert bool((d <= 0.06 + 0.03 * b.abs()).all()), (i, float(d.max()))
+        rms = max(1.0, float(b.pow(2).mean().sqrt()))
+        assert bool((d <= 0.05 * rms + 0.03 * b.abs()).all()), (i, float(d.max()), rms)
     assert z.shape == z_ref.shape
     d = (z - z_ref).abs()
     report["conf_cls"] = float(d[..., 4:].max())
