@@ -1,0 +1,38 @@
+"""Multi-GPU host logic: the forward shards by image pair -- one process per GPU, weights
+replicated, NO data-path collective.  ``torch.distributed`` is used only to agree on the partition, to
+reduce timings (max over ranks) and, optionally, to gather the decoded detections on one rank."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_pairs: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition of ``n_pairs`` image pairs (first ``n % world`` ranks get one more)."""
+    base, rem = divmod(n_pairs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Device-timed durations are reported as the max over ranks."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_detections(z_local: torch.Tensor, n_pairs: int) -> List[torch.Tensor]:
+    """Optional: collect every rank's decoded ``z`` shard (rank order == pair order).  Returns the list of
+    shards on every rank; shards may differ in batch size by one pair."""
+    world = dist.get_world_size()
+    bounds = [shard_bounds(n_pairs, world, r) for r in range(world)]
+    cap = max(hi - lo for lo, hi in bounds)                 # equal-size buffers (gloo/nccl all_gather contract)
+    padded = torch.zeros((cap,) + tuple(z_local.shape[1:]), dtype=z_local.dtype, device=z_local.device)
+    padded[: z_local.shape[0]] = z_local
+    outs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(outs, padded)
+    return [o[: hi - lo] for o, (lo, hi) in zip(outs, bounds)]
