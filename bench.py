@@ -94,13 +94,22 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Threads the process may actually use (cgroup/affinity aware; os.cpu_count() over-subscribes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
 def cpu_baseline(seconds_budget=20.0, batch=1):
     """The oracle port of the reference forward on the host cores: batch-1 forwards of the headline graph."""
     import torch
     from oracle import cft_oracle as O
     pkg = importlib.import_module("multispectral-object-detection_b200")
     cfg = pkg.named_config(CFG_NAME)
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     sd = O.init_state(cfg, seed=0)
     x, x2 = O.make_inputs(batch, H, W, seed=1)
     O.forward(sd, cfg, x, x2)                       # warm-up
@@ -121,7 +130,7 @@ def run_reference(args, rank):
     from oracle import cft_oracle as O
     pkg = importlib.import_module("multispectral-object-detection_b200")
     cfg = pkg.named_config(CFG_NAME)
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     sd = O.init_state(cfg, seed=0)
     b = 1                                             # bounded sample per step
     x, x2 = O.make_inputs(b, H, W, seed=1)

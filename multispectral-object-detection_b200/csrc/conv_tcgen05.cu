@@ -16,6 +16,8 @@
 //
 // Replaces the cuDNN/cuBLAS calls the reference reaches through nn.Conv2d / nn.Linear
 // (models/common.py:41-50,450-453,533-536; models/yolo_test.py:46).
+#include <stdlib.h>
+
 #include "cft_common.cuh"
 
 namespace {
@@ -29,11 +31,14 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 192 * 1024;   // operand ring
+constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
+constexpr int kNumStageC = 2;
 
 struct __align__(64) TensorMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap c;   // output (TMA store), box (32 channels, TW, TH, 1)
 };
 
 struct ConvParams {
@@ -41,7 +46,7 @@ struct ConvParams {
   int taps, kchunks, stride;
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
-  int act, out_f32;
+  int act, out_f32, tma_store;
   int ldy, y_coff, ldr, r_coff;
   const float* bias;
   void* y;
@@ -106,6 +111,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
@@ -186,7 +205,8 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const uint32_t b_tile_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * kATileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + stages * b_tile_bytes);
+  uint8_t* smem_c = smem_b + stages * b_tile_bytes;   // b_tile_bytes is a multiple of 2048 -> 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kNumStageC * kStageCBytes);
   uint64_t* full_bar = bars;                   // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;     // [kMaxStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue
@@ -196,6 +216,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   if (threadIdx.x == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
+    if (p.tma_store) prefetch_tmap(&maps.c);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -292,6 +313,8 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     const int ty_in = row / p.TW, tx_in = row - ty_in * p.TW;
+    const int epi_tid = threadIdx.x - 128;
+    uint32_t store_idx = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int oy = t.y0 + ty_in, ox = t.x0 + tx_in;
@@ -303,50 +326,80 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
-        if (valid) {
+        uint8_t* stage = smem_c + (store_idx & 1) * kStageCBytes;
+        if (p.tma_store) {
+          // the store issued two chunks ago was the last reader of this staging buffer
+          if (epi_tid == 0) bulk_wait_read<1>();
+          epi_bar_sync();
+        }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = c0 + j;
-            const int n = t.n0 + col;
-            if (col < p.block_n && n < p.Cout) {
-              float f[8];
+        for (int j = 0; j < 32; j += 8) {
+          const int col = c0 + j;
+          const int n = t.n0 + col;
+          const bool in_range = (col < p.block_n) && (n < p.Cout);
+          float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (p.act != CFT_ACT_NONE) {
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
+          if (in_range) {
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.act != CFT_ACT_NONE) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
-              }
+              for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+            }
+            if (p.res && valid) {
               if (p.out_f32) {
-                float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + n;
-                if (p.res) {
-                  const float* rp = reinterpret_cast<const float*>(p.res) + pix * p.ldr + p.r_coff + n;
-                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                }
-                *reinterpret_cast<float4*>(yp) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(yp + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                const float* rp = reinterpret_cast<const float*>(p.res) + pix * p.ldr + p.r_coff + n;
+                const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
               } else {
-                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + n;
-                if (p.res) {
-                  const __nv_bfloat16* rp =
-                      reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.ldr + p.r_coff + n;
-                  float r[8];
-                  unpack8(*reinterpret_cast<const bf16x8*>(rp), r);
+                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.ldr + p.r_coff + n;
+                float r[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(rp), r);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += r[i];
-                }
-                *reinterpret_cast<bf16x8*>(yp) = pack8(f);
+                for (int i = 0; i < 8; ++i) f[i] += r[i];
               }
             }
           }
+          if (p.tma_store) {
+            // staging tile = TMA box (32 channels x 128 pixels), hardware-swizzled rows:
+            //   bf16: 64 B rows, SWIZZLE_64B  (16B chunk ^= (row >> 1) & 3)
+            //   f32 : 128 B rows, SWIZZLE_128B (16B chunk ^= row & 7)
+            if (p.out_f32) {
+              const int ch = j >> 2;  // two 16 B chunks per 8 floats
+              float4* r0 = reinterpret_cast<float4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+              float4* r1 = reinterpret_cast<float4*>(stage + row * 128 + (((ch + 1) ^ (row & 7)) << 4));
+              *r0 = make_float4(f[0], f[1], f[2], f[3]);
+              *r1 = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              const int ch = j >> 3;
+              *reinterpret_cast<bf16x8*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)) = pack8(f);
+            }
+          } else if (valid && in_range) {
+            if (p.out_f32) {
+              float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + n;
+              *reinterpret_cast<float4*>(yp) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(yp + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + n;
+              *reinterpret_cast<bf16x8*>(yp) = pack8(f);
+            }
+          }
+        }
+        if (p.tma_store) {
+          fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA (async proxy)
+          epi_bar_sync();
+          if (epi_tid == 0) {
+            tma_store_4d(&maps.c, stage, t.n0 + c0, t.x0, t.y0, t.b);   // OOB pixels/channels are clipped
+            bulk_commit();
+          }
+          ++store_idx;
         }
       }
       tc_fence_before();
@@ -355,6 +408,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (p.tma_store && epi_tid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
   }
 
   tc_fence_before();
@@ -380,16 +434,16 @@ EncodeTiledFn get_encode() {
 }
 
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+               CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return CFT_E_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dt, rank, const_cast<void*>(base), dims, strides_b, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r,
               rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
@@ -407,7 +461,7 @@ int pick_block_n(int cout) {
   int nb = (cout + 255) / 256;
   for (;; ++nb) {
     if (nb > cout / 16) break;
-    if (cout % nb == 0 && (cout / nb) % 16 == 0 && cout / nb <= 256) return cout / nb;
+    if (cout % nb == 0 && (cout / nb) % 32 == 0 && cout / nb <= 256) return cout / nb;
     if (nb > 64) break;
   }
   return 256;
@@ -434,6 +488,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 }
 
 bool g_attr_set = false;
+const bool g_direct_store = getenv("CFT_DIRECT_STORE") != nullptr;   // debug: per-thread global stores
 
 }  // namespace
 
@@ -478,6 +533,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.act = a->act;
   p.out_f32 = a->out_dtype == CFT_DT_F32;
+  p.tma_store = g_direct_store ? 0 : 1;
   p.ldy = a->ldy;
   p.y_coff = a->y_coff;
   p.ldr = a->ldr;
@@ -520,10 +576,22 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     if (rc) return rc;
   }
 
-  const int smem_bytes = 1024 + p.stages * stage_bytes + 256;
+  if (p.tma_store) {
+    const cuuint64_t es = p.out_f32 ? 4 : 2;
+    const uint8_t* yb = reinterpret_cast<const uint8_t*>(a->y) + static_cast<size_t>(a->y_coff) * es;
+    cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)a->B};
+    cuuint64_t str[3] = {(cuuint64_t)a->ldy * es, (cuuint64_t)p.Wo * a->ldy * es, (cuuint64_t)p.Ho * p.Wo * a->ldy * es};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    rc = encode_map(&maps.c, yb, 4, dims, str, box,
+                    p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    p.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+
+  const int smem_bytes = 1024 + p.stages * stage_bytes + kNumStageC * kStageCBytes + 256;
   if (!g_attr_set) {
     rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         1024 + kSmemBudget + 256),
+                                         1024 + kSmemBudget + kNumStageC * kStageCBytes + 256),
                     "cudaFuncSetAttribute(conv_tcgen05)");
     if (rc) return rc;
     g_attr_set = true;

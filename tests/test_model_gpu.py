@@ -6,7 +6,8 @@ plus size-independent properties at BASELINE.json's full size (batch 32 @ 640x64
 Stated tolerance (bf16 activations/weights, fp32 accumulate, fp32 LN/softmax/residual stream/decode)
 against the fp32 reference, following SURVEY.md §8(c):
   raw heads : rel-L2 <= 2e-2 and |d| <= 0.05*max(1, rms(ref)) + 0.03*|ref| element-wise
-  decoded z : conf/cls |d| <= 2e-2 ; xy |d| <= 0.06*stride ; wh rel <= 8e-2 (+0.5 px)
+  decoded z : equals the oracle's fp32 decode of OUR raw heads (rtol 1e-5, atol 1e-4); conf/cls vs the
+              reference within |d raw|/4 (sigmoid slope)
   Detect row order / grid / anchors : bit-exact on identical raw heads (test_kernels_gpu.py).
 """
 import os
@@ -26,9 +27,13 @@ def build(cft, oracle, cfg_name, wseed):
     return cfg, sd, model.to(DEV)
 
 
-def check_outputs(z, raw, z_ref, raw_ref, strides=(8, 16, 32)):
+def check_outputs(z, raw, z_ref, raw_ref, oracle, anchor_grid):
+    """(1) raw heads vs the fp32 reference within the bf16 tolerance; (2) our decoded z equals the ORACLE's
+    decode of OUR raw heads to fp32 round-off (isolates the Detect arithmetic/indexing from upstream bf16
+    noise); (3) decoded z vs the reference: conf/cls within the sigmoid-propagated raw tolerance."""
     z, raw = z.float().cpu(), [r.float().cpu() for r in raw]
     report = {}
+    worst_raw = 0.0
     for i, (a, b) in enumerate(zip(raw, raw_ref)):
         assert a.shape == b.shape
         d = (a - b).abs()
@@ -37,16 +42,17 @@ def check_outputs(z, raw, z_ref, raw_ref, strides=(8, 16, 32)):
         assert rel_l2 <= 2e-2, (i, rel_l2)
         rms = max(1.0, float(b.pow(2).mean().sqrt()))
         assert bool((d <= 0.05 * rms + 0.03 * b.abs()).all()), (i, float(d.max()), rms)
+        worst_raw = max(worst_raw, float(d.max()))
     assert z.shape == z_ref.shape
-    d = (z - z_ref).abs()
-    report["conf_cls"] = float(d[..., 4:].max())
-    assert report["conf_cls"] <= 2e-2
-    # per-row stride: rows are level-major
-    rows = [r.shape[1] * r.shape[2] * r.shape[3] for r in raw_ref]
-    st = torch.cat([torch.full((n,), float(s)) for n, s in zip(rows, strides)])
-    assert bool((d[..., 0:2] <= 0.06 * st.view(1, -1, 1)).all()), float((d[..., 0:2] / st.view(1, -1, 1)).max())
-    assert bool((d[..., 2:4] <= 0.08 * z_ref[..., 2:4].abs() + 0.5).all()), float(d[..., 2:4].max())
+    z_dec = oracle.decode_heads(raw, anchor_grid)
+    assert torch.allclose(z, z_dec, rtol=1e-5, atol=1e-4), float((z - z_dec).abs().max())
+    report["conf_cls"] = float((z - z_ref)[..., 4:].abs().max())
+    assert report["conf_cls"] <= 0.25 * worst_raw + 1e-3            # |d sigmoid| <= |dv| / 4
     return report
+
+
+def anchor_grid_of(sd):
+    return sd["model.46.anchor_grid"]
 
 
 @pytest.mark.parametrize("name", ["s_vedai_b2_128x160", "s_vedai_b1_64x64_fused", "l_flir_b1_64x64",
@@ -61,7 +67,7 @@ def test_forward_matches_reference_golden(name, golden_dir, cft, oracle):
     with torch.no_grad():
         z, raw = model(x.to(DEV), x2.to(DEV))
     torch.cuda.synchronize()
-    rep = check_outputs(z, raw, g["z"], g["raw"])
+    rep = check_outputs(z, raw, g["z"], g["raw"], oracle, anchor_grid_of(sd))
     print(name, rep)
 
 
@@ -73,7 +79,7 @@ def test_forward_matches_cpu_oracle_s_320(cft, oracle):
     with torch.no_grad():
         z, raw = model(x.to(DEV), x2.to(DEV))
     torch.cuda.synchronize()
-    print(check_outputs(z, raw, z_ref, raw_ref))
+    print(check_outputs(z, raw, z_ref, raw_ref, oracle, anchor_grid_of(sd)))
 
 
 def test_forward_matches_cpu_oracle_l_640(cft, oracle):
@@ -85,7 +91,7 @@ def test_forward_matches_cpu_oracle_l_640(cft, oracle):
         z, raw = model(x.to(DEV), x2.to(DEV))
     torch.cuda.synchronize()
     assert z.shape == (1, 25200, 8)
-    print(check_outputs(z, raw, z_ref, raw_ref))
+    print(check_outputs(z, raw, z_ref, raw_ref, oracle, anchor_grid_of(sd)))
 
 
 def test_per_layer_parity_s(cft, oracle):
