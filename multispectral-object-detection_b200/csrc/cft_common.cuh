@@ -27,6 +27,9 @@ struct LaunchScope {
 
 int sm_count();
 
+// attention_tcgen05.cu: CFT_E_UNSUPPORTED when the shape is outside the tensor-core kernel.
+int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads, cudaStream_t stream);
+
 #define CFT_REQUIRE(cond, ...)                      \
   do {                                              \
     if (!(cond)) return ::cft::fail_arg(__VA_ARGS__); \

@@ -2,6 +2,8 @@
 //   adaptive-avg-pool tokeniser, LayerNorm, 128-token multi-head attention core,
 //   bilinear un-pool fused with Add2/Add, Detect permute + sigmoid/grid/anchor decode.
 // The six Linear layers per transformer block run on the tcgen05 GEMM (conv_tcgen05.cu).
+#include <stdlib.h>
+
 #include "cft_common.cuh"
 
 namespace {
@@ -325,6 +327,11 @@ extern "C" int cft_attention(const void* qkv, void* out, int B, int T, int C, in
   CFT_REQUIRE(qkv && out, "cft_attention: null pointer");
   CFT_REQUIRE(B > 0 && B <= 65535 && T > 0 && T <= 128 && heads > 0 && C % heads == 0 && (C / heads) % 8 == 0,
               "cft_attention: need T<=128 and head dim multiple of 8 (T %d C %d heads %d)", T, C, heads);
+  static const bool force_simt = getenv("CFT_ATTENTION_SIMT") != nullptr;   // debug / cross-check
+  if (!force_simt) {
+    const int rc = attention_tcgen05(qkv, out, B, T, C, heads, stream);
+    if (rc != CFT_E_UNSUPPORTED) return rc;
+  }
   const int dk = C / heads;
   const int smem = 3 * 128 * (dk + 2) * 2 + 128 * 129 * 4;
   CFT_REQUIRE(smem <= 220 * 1024, "cft_attention: head dim %d too large", dk);
