@@ -28,7 +28,8 @@ using namespace cft::ptx;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = one 128B swizzle row
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // TMA, MMA, TMEM-alloc, idle, 8 epilogue warps
+constexpr int kEpilogueWarps = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
@@ -41,11 +42,13 @@ struct __align__(64) TensorMaps {
   CUtensorMap a[4];
   CUtensorMap b;
   CUtensorMap c;   // output (TMA store), box (32 channels, TW, TH, 1)
+  CUtensorMap r;   // residual (TMA load), same geometry as c
 };
 
 struct ConvParams {
   int B, Ho, Wo, Cout;
   int taps, kchunks, stride;
+  int kelems, layout;       // K elements per ring stage (16 / 32 / 64) and the matching UMMA swizzle code
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
   int act, out_f32, tma_store;
@@ -81,28 +84,31 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  const uint32_t b_tile_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.block_n) * 128u;   // ring slot size (>= bytes actually loaded)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * kATileBytes;
-  uint8_t* smem_c = smem_b + stages * b_tile_bytes;   // b_tile_bytes is a multiple of 2048 -> 1024-aligned
+  uint8_t* smem_c = smem_b + stages * b_stage_bytes;  // b_stage_bytes is a multiple of 2048 -> 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kNumStageC * kStageCBytes);
-  uint64_t* full_bar = bars;                   // [kMaxStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + kMaxStages;     // [kMaxStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;      // [2] MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2; // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2] epilogue -> MMA
+  uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2] residual TMA -> epilogue group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
     if (p.tma_store) prefetch_tmap(&maps.c);
+    if (p.tma_store && p.res) prefetch_tmap(&maps.r);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpilogueWarps);   // one arrive per epilogue warp
+      mbar_init(&res_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -113,12 +119,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   const int k_iters = p.taps * p.kchunks;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.kelems) * 2u;   // operand tile row: 32 / 64 / 128 B
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH) * 128u + b_tile_bytes;
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH + p.block_n) * row_bytes;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       for (int tap = 0; tap < p.taps; ++tap) {
@@ -139,9 +146,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (lane == 0) {
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * kBlockK, t.x0 + dx,
+            tma_load_4d(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
                         t.y0 + dy, t.b);
-            tma_load_3d(smem_b + stage * b_tile_bytes, &maps.b, &full_bar[stage], kc * kBlockK, tap, t.n0);
+            tma_load_3d(smem_b + stage * b_stage_bytes, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
           }
           __syncwarp();
           if (++stage == stages) {
@@ -158,6 +165,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t idesc = umma_idesc(static_cast<uint32_t>(p.block_n));
+    const uint32_t sbo = 8u * row_bytes;               // 8-row group pitch of the swizzled K-major tile
+    const uint32_t layout = static_cast<uint32_t>(p.layout);
+    const int ksteps = p.kelems / 16;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
@@ -167,13 +177,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * b_tile_bytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32), umma_smem_desc(b_addr + k * 32), idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
+          const uint32_t b_addr = smem_u32(smem_b + stage * b_stage_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 0, sbo, layout), umma_desc(b_addr + k * 32, 0, sbo, layout),
+                      idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);               // smem slot free once these MMAs retire
+          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
           if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
@@ -186,100 +195,149 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;     // accumulator row = pixel within the tile
+    // ===================== epilogue: 2 column groups x 4 warps =====================
+    const int ew = warp - 4;
+    const int grp = ew >> 2;               // which half of the N columns
+    const int q = warp & 3;                // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;         // accumulator row = pixel within the tile
+    const int gtid = (ew & 3) * 32 + lane; // thread index within the group
+    uint8_t* stage_c = smem_c + grp * kStageCBytes;
+    uint64_t* rbar = &res_bar[grp];
+    uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int ty_in = row / p.TW, tx_in = row - ty_in * p.TW;
-    const int epi_tid = threadIdx.x - 128;
-    uint32_t store_idx = 0;
+    const int chunks_total = (p.block_n + 31) >> 5;                  // 32-column chunks
+    const int c_begin = grp == 0 ? 0 : (chunks_total + 1) >> 1;
+    const int c_end = grp == 0 ? (chunks_total + 1) >> 1 : chunks_total;
+    const int cps = p.out_f32 ? 1 : 2;                               // chunks per staging buffer (16 KiB)
+    const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
+    const uint32_t c_chunk_stride = 128u * c_row_bytes;
+    const uint32_t c_box_bytes = static_cast<uint32_t>(p.TW * p.TH) * c_row_bytes;
+    const bool use_res_tma = p.tma_store && p.res != nullptr;
+    const int bar_id = 1 + grp;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int oy = t.y0 + ty_in, ox = t.x0 + tx_in;
       const bool valid = (ty_in < p.TH) && (oy < p.Ho) && (ox < p.Wo);
       const size_t pix = (static_cast<size_t>(t.b) * p.Ho + oy) * p.Wo + ox;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
-        uint8_t* stage = smem_c + (store_idx & 1) * kStageCBytes;
+      bool waited_full = false;
+      for (int sg = c_begin; sg < c_end; sg += cps) {
+        const int nch = (c_end - sg) < cps ? (c_end - sg) : cps;
         if (p.tma_store) {
-          // the store issued two chunks ago was the last reader of this staging buffer
-          if (epi_tid == 0) bulk_wait_read<1>();
-          epi_bar_sync();
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int col = c0 + j;
-          const int n = t.n0 + col;
-          const bool in_range = (col < p.block_n) && (n < p.Cout);
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
-          if (in_range) {
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            if (p.act != CFT_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
-            }
-            if (p.res && valid) {
-              if (p.out_f32) {
-                const float* rp = reinterpret_cast<const float*>(p.res) + pix * p.ldr + p.r_coff + n;
-                const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-              } else {
-                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.ldr + p.r_coff + n;
-                float r[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(rp), r);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] += r[i];
-              }
+          // acquire the staging buffer: earlier stores out of it have been read; prefetch the residual tile
+          if (gtid == 0) {
+            bulk_wait_read<0>();
+            if (use_res_tma) {
+              mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
+              for (int i = 0; i < nch; ++i)
+                tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
             }
           }
-          if (p.tma_store) {
-            // staging tile = TMA box (32 channels x 128 pixels), hardware-swizzled rows:
-            //   bf16: 64 B rows, SWIZZLE_64B  (16B chunk ^= (row >> 1) & 3)
-            //   f32 : 128 B rows, SWIZZLE_128B (16B chunk ^= row & 7)
-            if (p.out_f32) {
-              const int ch = j >> 2;  // two 16 B chunks per 8 floats
-              float4* r0 = reinterpret_cast<float4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
-              float4* r1 = reinterpret_cast<float4*>(stage + row * 128 + (((ch + 1) ^ (row & 7)) << 4));
-              *r0 = make_float4(f[0], f[1], f[2], f[3]);
-              *r1 = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              const int ch = j >> 3;
-              *reinterpret_cast<bf16x8*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)) = pack8(f);
+          named_bar_sync(bar_id, 128);
+        }
+        if (!waited_full) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          waited_full = true;
+        }
+        if (use_res_tma) {
+          mbar_wait(rbar, res_phase);
+          res_phase ^= 1u;
+        }
+        for (int ci = 0; ci < nch; ++ci) {
+          const int c0 = (sg + ci) * 32;
+          uint8_t* stage = stage_c + ci * c_chunk_stride;
+          uint32_t v[32];
+          tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int col = c0 + j;
+            const int n = t.n0 + col;
+            const bool in_range = (col < p.block_n) && (n < p.Cout);
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
+            if (in_range) {
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.act != CFT_ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+              }
+              if (p.res && !p.tma_store && valid) {       // debug path: residual straight from global
+                if (p.out_f32) {
+                  const float* rp = reinterpret_cast<const float*>(p.res) + pix * p.ldr + p.r_coff + n;
+                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                } else {
+                  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.ldr + p.r_coff + n;
+                  float r[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(rp), r);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += r[i];
+                }
+              }
             }
-          } else if (valid && in_range) {
-            if (p.out_f32) {
-              float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + n;
-              *reinterpret_cast<float4*>(yp) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(yp + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + n;
-              *reinterpret_cast<bf16x8*>(yp) = pack8(f);
+            if (p.tma_store) {
+              // staging tile = TMA box (32 channels x TW x TH), hardware-swizzled rows:
+              //   bf16: 64 B rows, SWIZZLE_64B  (16 B chunk ^= (row >> 1) & 3)
+              //   f32 : 128 B rows, SWIZZLE_128B (16 B chunk ^= row & 7)
+              // The residual tile (if any) was TMA-loaded into the same positions: add in place.
+              if (p.out_f32) {
+                const int ch = j >> 2;  // two 16 B chunks per 8 floats
+                float4* s0 = reinterpret_cast<float4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+                float4* s1 = reinterpret_cast<float4*>(stage + row * 128 + (((ch + 1) ^ (row & 7)) << 4));
+                if (use_res_tma) {
+                  const float4 r0 = *s0, r1 = *s1;
+                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                }
+                *s0 = make_float4(f[0], f[1], f[2], f[3]);
+                *s1 = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                const int ch = j >> 3;
+                bf16x8* s0 = reinterpret_cast<bf16x8*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+                if (use_res_tma) {
+                  float r[8];
+                  unpack8(*s0, r);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += r[i];
+                }
+                *s0 = pack8(f);
+              }
+            } else if (valid && in_range) {
+              if (p.out_f32) {
+                float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + n;
+                *reinterpret_cast<float4*>(yp) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(yp + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + n;
+                *reinterpret_cast<bf16x8*>(yp) = pack8(f);
+              }
             }
           }
         }
         if (p.tma_store) {
           fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA (async proxy)
-          epi_bar_sync();
-          if (epi_tid == 0) {
-            tma_store_4d(&maps.c, stage, t.n0 + c0, t.x0, t.y0, t.b);   // OOB pixels/channels are clipped
+          named_bar_sync(bar_id, 128);
+          if (gtid == 0) {
+            for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
+              tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
             bulk_commit();
           }
-          ++store_idx;
         }
+      }
+      if (!waited_full) {               // a group with no columns still keeps the accumulator handshake in step
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
@@ -287,7 +345,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (p.tma_store && epi_tid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
+    if (p.tma_store && gtid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
   }
 
   tc_fence_before();
@@ -382,7 +440,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
               "cft_conv2d: Cin/ldx/x_coff must be multiples of 8 (got %d/%d/%d)", a->Cin, a->ldx, a->x_coff);
   CFT_REQUIRE(a->Cout % 8 == 0 && a->ldy % 8 == 0 && a->y_coff % 8 == 0,
               "cft_conv2d: Cout/ldy/y_coff must be multiples of 8 (got %d/%d/%d)", a->Cout, a->ldy, a->y_coff);
-  CFT_REQUIRE(!a->res || (a->ldr % 8 == 0 && a->r_coff % 8 == 0), "cft_conv2d: residual ld/coff must be multiples of 8");
+  CFT_REQUIRE(!a->res || (a->ldr % 8 == 0 && a->r_coff % 8 == 0 && reinterpret_cast<uintptr_t>(a->res) % 16 == 0),
+              "cft_conv2d: residual ld/coff must be multiples of 8 and the pointer 16-byte aligned");
   CFT_REQUIRE(a->x_coff + a->Cin <= a->ldx && a->y_coff + a->Cout <= a->ldy, "cft_conv2d: channel slice out of range");
   CFT_REQUIRE(reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->w) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(a->y) % 16 == 0,
@@ -397,7 +456,9 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.Wo = (a->W + s - 1) / s;
   p.Cout = a->Cout;
   p.taps = a->k * a->k;
-  p.kchunks = (a->Cin + kBlockK - 1) / kBlockK;
+  p.kelems = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
+  p.layout = p.kelems == 64 ? 2 : (p.kelems == 32 ? 4 : 6);   // UMMA LayoutType: SW128 / SW64 / SW32
+  p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
   p.stride = s;
   pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
@@ -426,12 +487,14 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a->x) + a->x_coff;
   const cuuint64_t eb = 2;
   int rc;
+  const CUtensorMapSwizzle op_swz = p.kelems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                   : (p.kelems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   if (s == 1) {
     cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
     cuuint64_t str[3] = {(cuuint64_t)a->ldx * eb, (cuuint64_t)a->W * a->ldx * eb,
                          (cuuint64_t)a->H * a->W * a->ldx * eb};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    rc = encode_map(&maps.a[0], xb, 4, dims, str, box);
+    cuuint32_t box[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    rc = encode_map(&maps.a[0], xb, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
     if (rc) return rc;
     maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
   } else {
@@ -440,9 +503,9 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)(a->W / 2), (cuuint64_t)(a->H / 2), (cuuint64_t)a->B};
         cuuint64_t str[3] = {(cuuint64_t)2 * a->ldx * eb, (cuuint64_t)2 * a->W * a->ldx * eb,
                              (cuuint64_t)a->H * a->W * a->ldx * eb};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
         const __nv_bfloat16* base = xb + (static_cast<size_t>(py) * a->W + px) * a->ldx;
-        rc = encode_map(&maps.a[py * 2 + px], base, 4, dims, str, box);
+        rc = encode_map(&maps.a[py * 2 + px], base, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
         if (rc) return rc;
       }
   }
@@ -450,8 +513,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     const int cin_p = round_up(a->Cin, 8);
     cuuint64_t dims[3] = {(cuuint64_t)a->Cin, (cuuint64_t)p.taps, (cuuint64_t)a->Cout};
     cuuint64_t str[2] = {(cuuint64_t)cin_p * eb, (cuuint64_t)p.taps * cin_p * eb};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)p.block_n};
-    rc = encode_map(&maps.b, a->w, 3, dims, str, box);
+    cuuint32_t box[3] = {(cuuint32_t)p.kelems, 1, (cuuint32_t)p.block_n};
+    rc = encode_map(&maps.b, a->w, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
     if (rc) return rc;
   }
 
@@ -465,6 +528,14 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
                     p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                     p.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
+    if (a->res) {
+      const uint8_t* rb = reinterpret_cast<const uint8_t*>(a->res) + static_cast<size_t>(a->r_coff) * es;
+      cuuint64_t rstr[3] = {(cuuint64_t)a->ldr * es, (cuuint64_t)p.Wo * a->ldr * es, (cuuint64_t)p.Ho * p.Wo * a->ldr * es};
+      rc = encode_map(&maps.r, rb, 4, dims, rstr, box,
+                      p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      p.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
   }
 
   const int smem_bytes = 1024 + p.stages * stage_bytes + kNumStageC * kStageCBytes + 256;

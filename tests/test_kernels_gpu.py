@@ -55,6 +55,10 @@ CONV_CASES = [
     (1, 512, 24, 20, 20, 1, 1, 0, False),       # Detect-style N = 24
     (2, 1024, 1024, 8, 8, 1, 1, 1, False),      # 16 k-chunks, 4 n-blocks
     (1, 320, 640, 8, 12, 1, 1, 0, False),       # N = 640 -> 4 x 160
+    (2, 32, 64, 24, 40, 3, 1, 1, True),         # 64 B operand rows (SWIZZLE_64B ring), residual via TMA
+    (2, 16, 32, 32, 32, 3, 2, 1, False),        # 32 B operand rows (SWIZZLE_32B ring), stride 2
+    (1, 64, 96, 20, 20, 3, 1, 1, True),         # 3 column chunks: uneven split over the 2 epilogue groups
+    (32, 128, 128, 80, 80, 3, 1, 1, True),      # full-size C3 bottleneck conv (batch 32): many tiles per CTA
 ]
 
 
