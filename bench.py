@@ -77,21 +77,27 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, smax, reasons, power = [], [], set(), []
+        sm, smax, reasons, power, rows = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                rows.append((float(f[1]), float(f[2]), float(f[3])))
             except ValueError:
                 continue
             for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        # the sampler runs from the first warm-up step to the end of the timed loop; "under load" = power well
+        # above idle (the timed loop alone can be shorter than one 200 ms sampling period)
+        pmax = max((r[2] for r in rows), default=0.0)
+        load = [r for r in rows if r[2] >= 0.6 * pmax] or rows
+        sm, smax, power = [r[0] for r in load], [r[1] for r in load], [r[2] for r in load]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(rows), "samples_under_load": len(load),
+                "reasons": sorted(reasons)}
 
 
 def host_threads():
@@ -214,6 +220,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- warm-up (also builds packed weights) ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for _ in range(W_):
             z, _ = step()
@@ -250,12 +259,9 @@ def main():
             step()
 
     # ---------------- timed region: K steps, device-resident inputs ----------------
-    sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
         barrier()
-        if rank == 0:
-            sampler.start()
         e0.record()
         for _ in range(K):
             run_step()

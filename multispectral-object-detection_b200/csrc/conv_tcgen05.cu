@@ -51,6 +51,7 @@ struct ConvParams {
   int kelems, layout;       // K elements per ring stage (16 / 32 / 64) and the matching UMMA swizzle code
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
+  int m_tiles;              // spatial tiles = B * tiles_y * tiles_x; num_tiles counts (pairs of) m-tiles x n-blocks
   int act, out_f32, tma_store;
   int ldy, y_coff, ldr, r_coff;
   const float* bias;
@@ -61,21 +62,31 @@ struct ConvParams {
 struct TileCoord {
   int b, y0, x0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+// work item -> tile of this CTA.  With CTA pairs a work item is two consecutive spatial tiles (rank 0 / 1) of
+// one n-block; a pair's missing second tile (odd count) gets b = B: all-OOB loads (zero fill), clipped stores.
+template <int kCtas>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, int rank) {
   TileCoord t;
-  const int nb = tile % p.n_blocks;
-  int m = tile / p.n_blocks;
+  const int nb = work % p.n_blocks;
+  int m = (work / p.n_blocks) * kCtas + rank;
+  t.n0 = nb * p.block_n;
+  if (m >= p.m_tiles) {
+    t.b = p.B;
+    t.y0 = 0;
+    t.x0 = 0;
+    return t;
+  }
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
   t.b = m / p.tiles_y;
   t.y0 = ty * p.TH;
   t.x0 = tx * p.TW;
-  t.n0 = nb * p.block_n;
   return t;
 }
 
 // ------------------------------------------------------------------ the kernel
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -84,7 +95,11 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.block_n) * 128u;   // ring slot size (>= bytes actually loaded)
+  const int rank = kCtas == 2 ? static_cast<int>(cluster_ctarank()) : 0;    // CTA within the pair
+  const int work0 = kCtas == 2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int work_stride = kCtas == 2 ? (gridDim.x >> 1) : gridDim.x;
+  const int b_rows = p.block_n / kCtas;                                     // weight rows this CTA stages
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(b_rows) * 128u;      // ring slot size (>= bytes actually loaded)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * kATileBytes;
   uint8_t* smem_c = smem_b + stages * b_stage_bytes;  // b_stage_bytes is a multiple of 2048 -> 1024-aligned
@@ -102,19 +117,23 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     if (p.tma_store) prefetch_tmap(&maps.c);
     if (p.tma_store && p.res) prefetch_tmap(&maps.r);
     for (int i = 0; i < stages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kCtas);      // pair: both producers arrive on CTA 0's barrier
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpilogueWarps);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpilogueWarps * kCtas);   // one arrive per epilogue warp (of both CTAs)
       mbar_init(&res_bar[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if constexpr (kCtas == 2) tmem_alloc_2sm(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -125,9 +144,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH + p.block_n) * row_bytes;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH + b_rows) * row_bytes;   // per CTA
+    for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
+      const TileCoord t = decode_tile<kCtas>(p, tile, rank);
       for (int tap = 0; tap < p.taps; ++tap) {
         int mi = 0, dy = 0, dx = 0;
         if (p.taps == 9) {
@@ -145,10 +164,19 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (lane == 0) {
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
-                        t.y0 + dy, t.b);
-            tma_load_3d(smem_b + stage * b_stage_bytes, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
+            if constexpr (kCtas == 2) {
+              tma_load_4d_2sm(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
+                              t.y0 + dy, t.b);
+              tma_load_3d_2sm(smem_b + stage * b_stage_bytes, &maps.b, &full_bar[stage], kc * p.kelems, tap,
+                              t.n0 + rank * b_rows);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_bytes);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
+                          t.y0 + dy, t.b);
+              tma_load_3d(smem_b + stage * b_stage_bytes, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
+            }
           }
           __syncwarp();
           if (++stage == stages) {
@@ -158,17 +186,17 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (CTA 0 of a pair issues for both) =====================
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t idesc = umma_idesc(static_cast<uint32_t>(p.block_n));
+    const uint32_t idesc = umma_idesc_ex(128u * kCtas, static_cast<uint32_t>(p.block_n), 0, 0);
     const uint32_t sbo = 8u * row_bytes;               // 8-row group pitch of the swizzled K-major tile
     const uint32_t layout = static_cast<uint32_t>(p.layout);
     const int ksteps = p.kelems / 16;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
@@ -179,11 +207,18 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * b_stage_bytes);
           for (int k = 0; k < ksteps; ++k) {
-            umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 0, sbo, layout), umma_desc(b_addr + k * 32, 0, sbo, layout),
-                      idesc, (it > 0 || k > 0) ? 1u : 0u);
+            const uint64_t da = umma_desc(a_addr + k * 32, 0, sbo, layout);
+            const uint64_t db = umma_desc(b_addr + k * 32, 0, sbo, layout);
+            if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if constexpr (kCtas == 2) {
+            umma_commit_2sm(&empty_bar[stage]);                       // frees the slot in both CTAs
+            if (it == k_iters - 1) umma_commit_2sm(&tfull_bar[acc]);  // both CTAs' epilogues
+          } else {
+            umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+            if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == stages) {
@@ -216,10 +251,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const uint32_t c_box_bytes = static_cast<uint32_t>(p.TW * p.TH) * c_row_bytes;
     const bool use_res_tma = p.tma_store && p.res != nullptr;
     const int bar_id = 1 + grp;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
+      const TileCoord t = decode_tile<kCtas>(p, tile, rank);
       const int oy = t.y0 + ty_in, ox = t.x0 + tx_in;
-      const bool valid = (ty_in < p.TH) && (oy < p.Ho) && (ox < p.Wo);
+      const bool valid = (ty_in < p.TH) && (oy < p.Ho) && (ox < p.Wo) && (t.b < p.B);
       const size_t pix = (static_cast<size_t>(t.b) * p.Ho + oy) * p.Wo + ox;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
       bool waited_full = false;
@@ -341,7 +376,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the MMA issuer lives in CTA 0
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -349,8 +387,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();     // the peer may still be reading operands / arriving on this CTA's barriers
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -426,6 +469,8 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 
 bool g_attr_set = false;
 const bool g_direct_store = getenv("CFT_DIRECT_STORE") != nullptr;   // debug: per-thread global stores
+// CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
+const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
 }  // namespace
 
@@ -465,10 +510,17 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   p.block_n = pick_block_n(a->Cout);
   p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
-  const long long tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y * p.n_blocks;
-  CFT_REQUIRE(tiles < (1LL << 31), "cft_conv2d: too many tiles");
-  p.num_tiles = static_cast<int>(tiles);
-  const int stage_bytes = kATileBytes + p.block_n * 128;
+  const long long m_tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y;
+  CFT_REQUIRE(m_tiles * p.n_blocks < (1LL << 31), "cft_conv2d: too many tiles");
+  p.m_tiles = static_cast<int>(m_tiles);
+  // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem
+  // traffic per MMA -- worth it once the layer is tensor-bound (enough K work per tile) and has >= 2 tiles.
+  const int k_iters = p.taps * p.kchunks;
+  int ctas = (g_force_ctas == 1) ? 1 : 2;
+  if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
+  if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
+  p.num_tiles = static_cast<int>(((m_tiles + ctas - 1) / ctas) * p.n_blocks);
+  const int stage_bytes = kATileBytes + (p.block_n / ctas) * 128;
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.act = a->act;
@@ -513,7 +565,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     const int cin_p = round_up(a->Cin, 8);
     cuuint64_t dims[3] = {(cuuint64_t)a->Cin, (cuuint64_t)p.taps, (cuuint64_t)a->Cout};
     cuuint64_t str[2] = {(cuuint64_t)cin_p * eb, (cuuint64_t)p.taps * cin_p * eb};
-    cuuint32_t box[3] = {(cuuint32_t)p.kelems, 1, (cuuint32_t)p.block_n};
+    cuuint32_t box[3] = {(cuuint32_t)p.kelems, 1, (cuuint32_t)(p.block_n / ctas)};
     rc = encode_map(&maps.b, a->w, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
     if (rc) return rc;
   }
@@ -540,15 +592,39 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
 
   const int smem_bytes = 1024 + p.stages * stage_bytes + kNumStageC * kStageCBytes + 256;
   if (!g_attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         1024 + kSmemBudget + kNumStageC * kStageCBytes + 256),
-                    "cudaFuncSetAttribute(conv_tcgen05)");
+    const int max_smem = 1024 + kSmemBudget + kNumStageC * kStageCBytes + 256;
+    rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+                    "cudaFuncSetAttribute(conv_tcgen05<1>)");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+                    "cudaFuncSetAttribute(conv_tcgen05<2>)");
     if (rc) return rc;
     g_attr_set = true;
   }
-  int grid = sm_count();
-  if (grid > p.num_tiles) grid = p.num_tiles;
+  int units = sm_count() / ctas;           // persistent: one CTA (or CTA pair) per SM (pair)
+  if (units > p.num_tiles) units = p.num_tiles;
   LaunchScope ls(CFT_K_CONV_TCGEN05, stream);
-  cft_conv_tcgen05_kernel<<<grid, kThreads, smem_bytes, stream>>>(maps, p);
+  if (ctas == 1) {
+    cft_conv_tcgen05_kernel<1><<<units, kThreads, smem_bytes, stream>>>(maps, p);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(units * 2);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, cft_conv_tcgen05_kernel<2>, maps, p);
+    if (e != cudaSuccess) {
+      ls.finish("cft_conv2d launch");
+      return check_cuda(e, "cudaLaunchKernelEx(conv_tcgen05<2>)");
+    }
+  }
   return ls.finish("cft_conv2d launch");
 }
