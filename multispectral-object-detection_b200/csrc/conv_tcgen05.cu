@@ -37,6 +37,7 @@ constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 192 * 1024;   // operand ring
 constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
 constexpr int kNumStageC = 2;
+constexpr int kTailBytes = 256 + 1024;     // barriers + TMEM slot, bias staging
 
 struct __align__(64) TensorMaps {
   CUtensorMap a[4];
@@ -52,7 +53,7 @@ struct ConvParams {
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
   int m_tiles;              // spatial tiles = B * tiles_y * tiles_x; num_tiles counts (pairs of) m-tiles x n-blocks
-  int act, out_f32, tma_store;
+  int act, out_f32;
   int ldy, y_coff, ldr, r_coff;
   const float* bias;
   void* y;
@@ -110,12 +111,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2] epilogue -> MMA
   uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2] residual TMA -> epilogue group
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);   // [256] bias of the current n-block
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
-    if (p.tma_store) prefetch_tmap(&maps.c);
-    if (p.tma_store && p.res) prefetch_tmap(&maps.r);
+    prefetch_tmap(&maps.c);
+    if (p.res) prefetch_tmap(&maps.r);
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], kCtas);      // pair: both producers arrive on CTA 0's barrier
       mbar_init(&empty_bar[i], 1);
@@ -241,7 +243,6 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int ty_in = row / p.TW, tx_in = row - ty_in * p.TW;
     const int chunks_total = (p.block_n + 31) >> 5;                  // 32-column chunks
     const int c_begin = grp == 0 ? 0 : (chunks_total + 1) >> 1;
     const int c_end = grp == 0 ? (chunks_total + 1) >> 1 : chunks_total;
@@ -249,35 +250,38 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
     const uint32_t c_chunk_stride = 128u * c_row_bytes;
     const uint32_t c_box_bytes = static_cast<uint32_t>(p.TW * p.TH) * c_row_bytes;
-    const bool use_res_tma = p.tma_store && p.res != nullptr;
+    const bool use_res = p.res != nullptr;
+    int bias_n0 = -1;
     const int bar_id = 1 + grp;
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
-      const int oy = t.y0 + ty_in, ox = t.x0 + tx_in;
-      const bool valid = (ty_in < p.TH) && (oy < p.Ho) && (ox < p.Wo) && (t.b < p.B);
-      const size_t pix = (static_cast<size_t>(t.b) * p.Ho + oy) * p.Wo + ox;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
       bool waited_full = false;
       for (int sg = c_begin; sg < c_end; sg += cps) {
         const int nch = (c_end - sg) < cps ? (c_end - sg) : cps;
-        if (p.tma_store) {
-          // acquire the staging buffer: earlier stores out of it have been read; prefetch the residual tile
-          if (gtid == 0) {
-            bulk_wait_read<0>();
-            if (use_res_tma) {
-              mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
-              for (int i = 0; i < nch; ++i)
-                tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
-            }
+        // acquire the staging buffer: earlier stores out of it have been read; prefetch the residual tile
+        if (gtid == 0) {
+          bulk_wait_read<0>();
+          if (use_res) {
+            mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
+            for (int i = 0; i < nch; ++i)
+              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
           }
-          named_bar_sync(bar_id, 128);
         }
+        if (t.n0 != bias_n0) {          // (re)stage this n-block's bias; published by the barrier below
+          for (int i = gtid; i < (c_end - c_begin) * 32; i += 128) {
+            const int n = t.n0 + c_begin * 32 + i;
+            bias_s[c_begin * 32 + i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+          }
+          bias_n0 = t.n0;
+        }
+        named_bar_sync(bar_id, 128);
         if (!waited_full) {
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
           waited_full = true;
         }
-        if (use_res_tma) {
+        if (use_res) {
           mbar_wait(rbar, res_phase);
           res_phase ^= 1u;
         }
@@ -286,88 +290,60 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           uint8_t* stage = stage_c + ci * c_chunk_stride;
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
+          // bias (staged in smem once per n-block; zero beyond Cout) + activation on all 32 columns: straight-line,
+          // 32 independent dependency chains (columns past Cout/block_n hold garbage that the TMA store clips).
+          float f[32];
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = c0 + j;
-            const int n = t.n0 + col;
-            const bool in_range = (col < p.block_n) && (n < p.Cout);
-            float f[8];
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = bs[i];
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+          }
+          if (p.act == CFT_ACT_SILU) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j + i]);
-            if (in_range) {
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            for (int i = 0; i < 32; ++i) f[i] = silu_fast(f[i]);
+          } else if (p.act == CFT_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+          }
+          // staging tile = TMA box (32 channels x TW x TH), hardware-swizzled rows:
+          //   bf16: 64 B rows, SWIZZLE_64B  (16 B chunk ^= (row >> 1) & 3)
+          //   f32 : 128 B rows, SWIZZLE_128B (16 B chunk ^= row & 7)
+          // The residual tile (if any) was TMA-loaded into the same positions: add in place.
+          if (p.out_f32) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              float4* s0 = reinterpret_cast<float4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+              float4 o = make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
+              if (use_res) {
+                const float4 r0 = *s0;
+                o.x += r0.x; o.y += r0.y; o.z += r0.z; o.w += r0.w;
               }
-              if (p.act != CFT_ACT_NONE) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
-              }
-              if (p.res && !p.tma_store && valid) {       // debug path: residual straight from global
-                if (p.out_f32) {
-                  const float* rp = reinterpret_cast<const float*>(p.res) + pix * p.ldr + p.r_coff + n;
-                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                } else {
-                  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.ldr + p.r_coff + n;
-                  float r[8];
-                  unpack8(*reinterpret_cast<const bf16x8*>(rp), r);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += r[i];
-                }
-              }
+              *s0 = o;
             }
-            if (p.tma_store) {
-              // staging tile = TMA box (32 channels x TW x TH), hardware-swizzled rows:
-              //   bf16: 64 B rows, SWIZZLE_64B  (16 B chunk ^= (row >> 1) & 3)
-              //   f32 : 128 B rows, SWIZZLE_128B (16 B chunk ^= row & 7)
-              // The residual tile (if any) was TMA-loaded into the same positions: add in place.
-              if (p.out_f32) {
-                const int ch = j >> 2;  // two 16 B chunks per 8 floats
-                float4* s0 = reinterpret_cast<float4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
-                float4* s1 = reinterpret_cast<float4*>(stage + row * 128 + (((ch + 1) ^ (row & 7)) << 4));
-                if (use_res_tma) {
-                  const float4 r0 = *s0, r1 = *s1;
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                }
-                *s0 = make_float4(f[0], f[1], f[2], f[3]);
-                *s1 = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                const int ch = j >> 3;
-                bf16x8* s0 = reinterpret_cast<bf16x8*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-                if (use_res_tma) {
-                  float r[8];
-                  unpack8(*s0, r);
+          } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += r[i];
-                }
-                *s0 = pack8(f);
+            for (int ch = 0; ch < 4; ++ch) {
+              bf16x8* s0 = reinterpret_cast<bf16x8*>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+              if (use_res) {
+                float r[8];
+                unpack8(*s0, r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[8 * ch + i] += r[i];
               }
-            } else if (valid && in_range) {
-              if (p.out_f32) {
-                float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + n;
-                *reinterpret_cast<float4*>(yp) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(yp + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + n;
-                *reinterpret_cast<bf16x8*>(yp) = pack8(f);
-              }
+              *s0 = pack8(f + 8 * ch);
             }
           }
         }
-        if (p.tma_store) {
-          fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(bar_id, 128);
-          if (gtid == 0) {
-            for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
-              tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
-            bulk_commit();
-          }
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(bar_id, 128);
+        if (gtid == 0) {
+          for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
+            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
+          bulk_commit();
         }
       }
       if (!waited_full) {               // a group with no columns still keeps the accumulator handshake in step
@@ -383,7 +359,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (p.tma_store && gtid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
+    if (gtid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
   }
 
   tc_fence_before();
@@ -468,7 +444,6 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 }
 
 bool g_attr_set = false;
-const bool g_direct_store = getenv("CFT_DIRECT_STORE") != nullptr;   // debug: per-thread global stores
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
@@ -525,7 +500,6 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.act = a->act;
   p.out_f32 = a->out_dtype == CFT_DT_F32;
-  p.tma_store = g_direct_store ? 0 : 1;
   p.ldy = a->ldy;
   p.y_coff = a->y_coff;
   p.ldr = a->ldr;
@@ -570,7 +544,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     if (rc) return rc;
   }
 
-  if (p.tma_store) {
+  {
     const cuuint64_t es = p.out_f32 ? 4 : 2;
     const uint8_t* yb = reinterpret_cast<const uint8_t*>(a->y) + static_cast<size_t>(a->y_coff) * es;
     cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)a->B};
@@ -590,9 +564,9 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     }
   }
 
-  const int smem_bytes = 1024 + p.stages * stage_bytes + kNumStageC * kStageCBytes + 256;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + kNumStageC * kStageCBytes + kTailBytes;
   if (!g_attr_set) {
-    const int max_smem = 1024 + kSmemBudget + kNumStageC * kStageCBytes + 256;
+    const int max_smem = 1024 + kSmemBudget + kNumStageC * kStageCBytes + kTailBytes;
     rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
                     "cudaFuncSetAttribute(conv_tcgen05<1>)");
     if (rc) return rc;
