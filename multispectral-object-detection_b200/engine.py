@@ -1,0 +1,129 @@
+"""Serving-side executor for the two-stream forward: CUDA streams and graphs, no tracing compiler.
+
+``ForwardEngine`` wraps a ``Model`` for one fixed input geometry (batch, H, W, uint8 wire format
+``[B,6,H,W]`` = RGB||IR, reference ``utils/datasets.py:1272-1281`` / ``train.py:715-717``):
+
+* the whole 47-layer forward (~350 kernel launches) is captured once per buffer slot into a CUDA graph
+  (launch-bound at small batch) and replayed;
+* two device input/output slots + a copy stream: the host->device copy of batch i+1 and the
+  device->host copy of detections i-1 overlap the compute of batch i;
+* ``infer(host_u8)`` is the blocking call a user makes; ``submit()/collect()`` expose the pipeline.
+
+The reference has no counterpart (it launches eager PyTorch ops on the default stream, ``test.py:106-119``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from ._lib import CftError, launch_count
+
+
+class ForwardEngine:
+    def __init__(self, model, batch: int, height: int, width: int, device=None, slots: int = 2, use_graph: bool = True):
+        self.model = model.eval()
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise CftError("ForwardEngine needs a CUDA device (no CPU fallback)")
+        self.shape = (batch, 6, height, width)
+        self.slots = slots
+        self.use_graph = use_graph
+        self.compute = torch.cuda.Stream(self.device)
+        self.copy = torch.cuda.Stream(self.device)
+        self.x_dev = [torch.zeros(self.shape, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+        self.z_dev: List[Optional[torch.Tensor]] = [None] * slots
+        self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * slots
+        self.ev_in = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_done = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_free = [torch.cuda.Event() for _ in range(slots)]
+        self.z_host: List[Optional[torch.Tensor]] = [None] * slots
+        self.launches_per_forward = 0
+        self._next = 0
+        self._pending: List[int] = []
+        self._build()
+
+    # ------------------------------------------------------------------ setup
+    def _forward(self, s: int):
+        x = self.x_dev[s]
+        z, _ = self.model(x[:, :3], x[:, 3:])
+        return z
+
+    def _build(self):
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.stream(self.compute), torch.no_grad():
+            for _ in range(2):                      # warm-up: packs weights, sizes the allocator pools
+                self._forward(0)
+            n0 = launch_count()
+            self._forward(0)
+            self.launches_per_forward = launch_count() - n0
+        self.compute.synchronize()
+        for s in range(self.slots):
+            if self.use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g, stream=self.compute):
+                    self.z_dev[s] = self._forward(s)
+                self.graphs[s] = g
+            else:
+                with torch.cuda.stream(self.compute), torch.no_grad():
+                    self.z_dev[s] = self._forward(s)
+            self.z_host[s] = torch.empty(self.z_dev[s].shape, dtype=self.z_dev[s].dtype).pin_memory()
+            self.ev_free[s].record(self.compute)
+        self.compute.synchronize()
+
+    # ------------------------------------------------------------------ device-resident replay (kernel-only timing)
+    def run_resident(self, slot: int = 0):
+        """One forward over whatever is in the slot's device input buffer, on the engine's compute stream."""
+        with torch.cuda.stream(self.compute):
+            if self.use_graph:
+                self.graphs[slot].replay()
+            else:
+                with torch.no_grad():
+                    self.z_dev[slot] = self._forward(slot)
+        return self.z_dev[slot]
+
+    # ------------------------------------------------------------------ pipelined host->device->host path
+    def submit(self, host_u8: torch.Tensor) -> int:
+        """Queue one batch (uint8 [B,6,H,W], ideally pinned). Returns the slot to ``collect``."""
+        if tuple(host_u8.shape) != self.shape or host_u8.dtype != torch.uint8:
+            raise CftError(f"submit: expected uint8 {self.shape}, got {host_u8.dtype} {tuple(host_u8.shape)}")
+        s = self._next
+        self._next = (self._next + 1) % self.slots
+        if s in self._pending:
+            raise CftError("submit: all slots in flight; collect() first")
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.ev_free[s])           # slot's previous result has left the device
+            self.x_dev[s].copy_(host_u8, non_blocking=True)
+            self.ev_in[s].record(self.copy)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(self.ev_in[s])
+            if self.use_graph:
+                self.graphs[s].replay()
+            else:
+                with torch.no_grad():
+                    self.z_dev[s] = self._forward(s)
+            self.ev_done[s].record(self.compute)
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.ev_done[s])
+            self.z_host[s].copy_(self.z_dev[s], non_blocking=True)
+            self.ev_free[s].record(self.copy)
+        self._pending.append(s)
+        return s
+
+    def collect(self, slot: Optional[int] = None) -> torch.Tensor:
+        """Wait for the oldest (or the given) submitted batch; returns its detections z on the host (pinned)."""
+        if not self._pending:
+            raise CftError("collect: nothing submitted")
+        s = self._pending.pop(0) if slot is None else self._pending.pop(self._pending.index(slot))
+        self.ev_free[s].synchronize()
+        return self.z_host[s]
+
+    def infer(self, host_u8: torch.Tensor) -> torch.Tensor:
+        """Blocking convenience call: host uint8 batch in, host fp32 detections ``z [B, rows, no]`` out."""
+        return self.collect(self.submit(host_u8))
+
+    def drain(self):
+        while self._pending:
+            self.collect()
+        self.compute.synchronize()
+        self.copy.synchronize()

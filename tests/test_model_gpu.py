@@ -170,3 +170,29 @@ def test_channel_last_slices_and_inputs(cft, oracle):
         z16, _ = model(x.to(torch.bfloat16), x2.to(torch.bfloat16))
     torch.cuda.synchronize()
     assert torch.equal(z32, z16)     # the gather rounds fp32 -> bf16 exactly as .to(bfloat16) does
+
+
+def test_forward_engine_graph_pipeline(cft, oracle):
+    """ForwardEngine (CUDA-graph replay, double-buffered copy pipeline, uint8 wire format): every batch's result
+    equals the eager forward of the same batch, in submission order."""
+    cfg, sd, model = build(cft, oracle, "yolov5s_fusion_transformerx3_vedai", 13)
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.randint(0, 256, (2, 6, 96, 128), dtype=torch.uint8, generator=g).pin_memory() for _ in range(5)]
+    eng = cft.ForwardEngine(model, 2, 96, 128, device=DEV, slots=2)
+    assert eng.launches_per_forward > 100
+    outs = []
+    for i, hb in enumerate(batches):
+        if len(eng._pending) == eng.slots:
+            outs.append(eng.collect().clone())
+        eng.submit(hb)
+    while eng._pending:
+        outs.append(eng.collect().clone())
+    with torch.no_grad():
+        for hb, z in zip(batches, outs):
+            d = hb.to(DEV)
+            z_ref, _ = model(d[:, :3], d[:, 3:])
+            # uint8 /255 in-kernel == float input scaled by 1/255 then rounded to bf16
+            z_f, _ = model((d[:, :3].float() / 255.0), (d[:, 3:].float() / 255.0))
+            assert torch.equal(z, z_ref.cpu())
+            assert torch.equal(z_ref, z_f)
+    assert torch.equal(eng.infer(batches[0]), outs[0])
