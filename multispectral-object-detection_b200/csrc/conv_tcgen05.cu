@@ -165,7 +165,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         }
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (lane == 0) {
+          if (elect_one_sync()) {
             if constexpr (kCtas == 2) {
               tma_load_4d_2sm(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
                               t.y0 + dy, t.b);
@@ -195,8 +195,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t idesc = umma_idesc_ex(128u * kCtas, static_cast<uint32_t>(p.block_n), 0, 0);
-    const uint32_t sbo = 8u * row_bytes;               // 8-row group pitch of the swizzled K-major tile
-    const uint32_t layout = static_cast<uint32_t>(p.layout);
+    // smem operand descriptor: [0,14) start >> 4 | [32,46) SBO >> 4 | bit 46 version | [61,64) swizzle code
+    const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (static_cast<uint32_t>(p.layout) << 29);
+    const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
+    const uint32_t a_lo_stride = kATileBytes >> 4, b_lo_stride = b_stage_bytes >> 4;
     const int ksteps = p.kelems / 16;
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -205,14 +207,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * b_stage_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = umma_desc(a_addr + k * 32, 0, sbo, layout);
-            const uint64_t db = umma_desc(b_addr + k * 32, 0, sbo, layout);
-            if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
+          for (int k = 0; k < ksteps; ++k) {          // +32 B along K inside the swizzle atom = +2 in the address field
+            const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
+            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
+            if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
           if constexpr (kCtas == 2) {
             umma_commit_2sm(&empty_bar[stage]);                       // frees the slot in both CTAs
