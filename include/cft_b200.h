@@ -91,6 +91,12 @@ int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long lo
 int cft_maxpool_s1(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff,
                    int B, int H, int W, int C, int k, void* stream);
 
+/* SPP in one pass (models/common.py:160-165): three stride-1 max pools applied in cascade (windows k0, k1, k2;
+ * pool_9 = pool_5 o pool_5 and pool_13 = pool_5 o pool_9, so SPP's (5,9,13) is the cascade (5,5,5)); the result of
+ * stage i goes to channel slice y_coff_i of y.  C must be a multiple of 16; H*W*64 bytes of smem per CTA. */
+int cft_maxpool_cascade3(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff0, int y_coff1,
+                         int y_coff2, int B, int H, int W, int C, int k0, int k1, int k2, void* stream);
+
 /* nn.Upsample(None, 2, 'nearest') (yaml rows 33/37): [B,H,W,C] -> [B,2H,2W,C]. */
 int cft_upsample2x(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff,
                    int B, int H, int W, int C, void* stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "cft_conv2d_ref": ([C.POINTER(ConvArgs), _P], _I),
     "cft_focus_gather": ([_P, _I, _I, _I, _I, _LL, _P, _P], _I),
     "cft_maxpool_s1": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "cft_maxpool_cascade3": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_upsample2x": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_add": ([_P, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _I, _P], _I),
     "cft_copy": ([_P, _I, _I, _P, _I, _I, _LL, _I, _P], _I),

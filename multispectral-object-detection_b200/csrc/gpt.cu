@@ -234,6 +234,75 @@ __global__ void unpool_kernel(UnpoolArgs a) {
   }
 }
 
+
+// Row-blocked variant: one CTA per (image, output row, 64-channel chunk).  The two token rows that bracket the
+// output row are blended vertically once into smem (2 modalities x ha tokens x 64 channels, fp32); each thread
+// then does only the horizontal lerp for its (pixel, 8-channel vector) -- the feature maps are streamed once,
+// coalesced, and the token tensor is read ~H/va times less often than by the per-pixel kernel.
+constexpr int kUnpoolCC = 64;
+__global__ void unpool_rows_kernel(UnpoolArgs a) {
+  extern __shared__ float srow[];                 // [2][ha][kUnpoolCC]
+  const int y = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
+  const int cells = a.va * a.ha;
+  int y0, y1;
+  float ly;
+  bilin(y, a.va, a.H, &y0, &y1, &ly);
+  const int c_base = cc * kUnpoolCC;
+  const int cw = min(kUnpoolCC, a.C - c_base);    // channels in this chunk (multiple of 8)
+  for (int i = threadIdx.x; i < 2 * a.ha * (cw / 4); i += blockDim.x) {
+    const int c4 = i % (cw / 4);
+    const int t = i / (cw / 4);                   // m * ha + tx
+    const int m = t / a.ha, tx = t - m * a.ha;
+    const float* tb = a.tok + (static_cast<long long>(b) * 2 * cells + m * cells) * a.C + c_base + c4 * 4;
+    const float4 p0 = *reinterpret_cast<const float4*>(tb + static_cast<long long>(y0 * a.ha + tx) * a.C);
+    const float4 p1 = *reinterpret_cast<const float4*>(tb + static_cast<long long>(y1 * a.ha + tx) * a.C);
+    float4 r;
+    r.x = (1.f - ly) * p0.x + ly * p1.x;
+    r.y = (1.f - ly) * p0.y + ly * p1.y;
+    r.z = (1.f - ly) * p0.z + ly * p1.z;
+    r.w = (1.f - ly) * p0.w + ly * p1.w;
+    *reinterpret_cast<float4*>(srow + t * kUnpoolCC + c4 * 4) = r;
+  }
+  __syncthreads();
+  const int cv8 = cw / 8;
+  const long long row_pix = (static_cast<long long>(b) * a.H + y) * a.W;
+  for (int i = threadIdx.x; i < a.W * cv8; i += blockDim.x) {
+    const int cv = i % cv8, x = i / cv8;
+    int x0, x1;
+    float lx;
+    bilin(x, a.ha, a.W, &x0, &x1, &lx);
+    const long long pix = row_pix + x;
+    const int c = c_base + cv * 8;
+    float r[2][8];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float* s0 = srow + (m * a.ha + x0) * kUnpoolCC + cv * 8;
+      const float* s1 = srow + (m * a.ha + x1) * kUnpoolCC + cv * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[m][j] = (1.f - lx) * s0[j] + lx * s1[j];
+    }
+    if (a.x_rgb) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[0][j] += f[j];
+    }
+    if (a.x_ir) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[1][j] += f[j];
+    }
+    *reinterpret_cast<bf16x8*>(a.o_rgb + pix * a.ld_or + c) = pack8(r[0]);
+    *reinterpret_cast<bf16x8*>(a.o_ir + pix * a.ld_oi + c) = pack8(r[1]);
+    if (a.o_sum) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[0][j] += r[1][j];
+      *reinterpret_cast<bf16x8*>(a.o_sum + pix * a.ld_os + c) = pack8(r[0]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ Detect tail
 // One thread per (b, anchor, j, i).  Index math is integer-exact:
 //   raw[b][a][j][i][o], z row = z_row0 + a*ny*nx + j*nx + i, grid = (i, j)  (models/yolo_test.py:48-64)
@@ -368,9 +437,17 @@ extern "C" int cft_gpt_unpool(const float* tok, int B, int H, int W, int C, int 
   a.o_ir = reinterpret_cast<__nv_bfloat16*>(out_ir) + coff_oi;
   a.o_sum = out_sum ? reinterpret_cast<__nv_bfloat16*>(out_sum) + coff_os : nullptr;
   a.ld_or = ld_or; a.ld_oi = ld_oi; a.ld_os = ld_os;
-  const long long total = static_cast<long long>(B) * H * W * (C / 8);
   LaunchScope ls(CFT_K_UNPOOL, stream);
-  unpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+  const int chunks = (C + kUnpoolCC - 1) / kUnpoolCC;
+  if (H <= 65535 && chunks <= 65535 && B <= 65535 && ha <= 64) {
+    int threads = W * (kUnpoolCC / 8);
+    threads = threads > 512 ? 512 : (threads < 64 ? 64 : (threads + 31) / 32 * 32);
+    dim3 grid(H, chunks, B);
+    unpool_rows_kernel<<<grid, threads, 2 * ha * kUnpoolCC * sizeof(float), stream>>>(a);
+  } else {
+    const long long total = static_cast<long long>(B) * H * W * (C / 8);
+    unpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+  }
   return ls.finish("cft_gpt_unpool launch");
 }
 

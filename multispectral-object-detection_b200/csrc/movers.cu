@@ -91,6 +91,70 @@ __global__ void maxpool_s1_kernel(const __nv_bfloat16* __restrict__ x, int ldx, 
   }
 }
 
+
+// ------------------------------------------------------------------ SPP: cascade of stride-1 max pools, one pass
+// One CTA per (image, 16-channel group): the HxW plane of 16 channels (32 B per pixel = one full sector) is
+// staged in smem, then three separable k x k max pools are applied back to back (row pass + column pass each);
+// the result of every stage is written to its own channel slice.  pool_9 = pool_5(pool_5), pool_13 = pool_5(pool_9)
+// for stride-1 pools with -inf padding, so SPP's (5, 9, 13) is the cascade (5, 5, 5).
+struct __align__(16) bf16x16 {
+  bf16x8 lo, hi;
+};
+__device__ __forceinline__ bf16x8 max8(const bf16x8& a, const bf16x8& b) {
+  bf16x8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __hmax2(a.v[i], b.v[i]);
+  return r;
+}
+__global__ void maxpool_cascade_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y0,
+                                       __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2, int ldy, int H,
+                                       int W, int k0, int k1, int k2) {
+  extern __shared__ uint8_t sm_raw[];
+  bf16x16* bufA = reinterpret_cast<bf16x16*>(sm_raw);
+  bf16x16* bufB = bufA + H * W;
+  const int cg = blockIdx.x, b = blockIdx.y;
+  const int npix = H * W;
+  const long long img = static_cast<long long>(b) * npix;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+    const __nv_bfloat16* p = x + (img + i) * ldx + cg * 16;
+    bufA[i].lo = *reinterpret_cast<const bf16x8*>(p);
+    bufA[i].hi = *reinterpret_cast<const bf16x8*>(p + 8);
+  }
+  __syncthreads();
+  __nv_bfloat16* outs[3] = {y0, y1, y2};
+  const int ks[3] = {k0, k1, k2};
+  for (int st = 0; st < 3; ++st) {
+    const int r = ks[st] / 2;
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {      // row pass: A -> B
+      const int yy = i / W, xx = i - yy * W;
+      const int xa = max(xx - r, 0), xb = min(xx + r, W - 1);
+      bf16x16 m = bufA[yy * W + xa];
+      for (int q = xa + 1; q <= xb; ++q) {
+        const bf16x16 v = bufA[yy * W + q];
+        m.lo = max8(m.lo, v.lo);
+        m.hi = max8(m.hi, v.hi);
+      }
+      bufB[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {      // column pass: B -> A (+ global)
+      const int yy = i / W, xx = i - yy * W;
+      const int ya = max(yy - r, 0), yb = min(yy + r, H - 1);
+      bf16x16 m = bufB[ya * W + xx];
+      for (int q = ya + 1; q <= yb; ++q) {
+        const bf16x16 v = bufB[q * W + xx];
+        m.lo = max8(m.lo, v.lo);
+        m.hi = max8(m.hi, v.hi);
+      }
+      bufA[i] = m;
+      __nv_bfloat16* o = outs[st] + (img + i) * ldy + cg * 16;
+      *reinterpret_cast<bf16x8*>(o) = m.lo;
+      *reinterpret_cast<bf16x8*>(o + 8) = m.hi;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ nearest 2x upsample
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                                   int B, int H, int W, int C8) {
@@ -217,6 +281,37 @@ extern "C" int cft_maxpool_s1(const void* x, int ldx, int x_coff, void* y, int l
       reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx, reinterpret_cast<__nv_bfloat16*>(y) + y_coff, ldy, B, H,
       W, C / 8, k);
   return ls.finish("cft_maxpool_s1 launch");
+}
+
+
+extern "C" int cft_maxpool_cascade3(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff0, int y_coff1,
+                                    int y_coff2, int B, int H, int W, int C, int k0, int k1, int k2, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  int rc;
+  if ((rc = check_slice("cft_maxpool_cascade3", x, ldx, x_coff, C))) return rc;
+  if ((rc = check_slice("cft_maxpool_cascade3", y, ldy, y_coff0, C))) return rc;
+  if ((rc = check_slice("cft_maxpool_cascade3", y, ldy, y_coff1, C))) return rc;
+  if ((rc = check_slice("cft_maxpool_cascade3", y, ldy, y_coff2, C))) return rc;
+  CFT_REQUIRE(C % 16 == 0 && (k0 & 1) && (k1 & 1) && (k2 & 1) && k0 > 0 && k1 > 0 && k2 > 0,
+              "cft_maxpool_cascade3: C must be a multiple of 16 and the windows odd");
+  CFT_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "cft_maxpool_cascade3: bad shape");
+  const size_t smem = static_cast<size_t>(H) * W * 64;
+  CFT_REQUIRE(smem <= 200 * 1024, "cft_maxpool_cascade3: plane %dx%d too large for the smem-staged kernel", H, W);
+  static bool attr = false;
+  if (!attr) {
+    rc = check_cuda(cudaFuncSetAttribute(maxpool_cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                    "cudaFuncSetAttribute(maxpool_cascade)");
+    if (rc) return rc;
+    attr = true;
+  }
+  int threads = H * W;
+  threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
+  dim3 grid(C / 16, B);
+  LaunchScope ls(CFT_K_MAXPOOL, stream);
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+  maxpool_cascade_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx,
+                                                          yb + y_coff0, yb + y_coff1, yb + y_coff2, ldy, H, W, k0, k1, k2);
+  return ls.finish("cft_maxpool_cascade3 launch");
 }
 
 extern "C" int cft_upsample2x(const void* x, int ldx, int x_coff, void* y, int ldy, int y_coff, int B, int H, int W,

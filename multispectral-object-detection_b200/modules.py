@@ -190,15 +190,19 @@ class SPP(nn.Module):
         ks = [m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0] for m in self.m]
         cat = ops.empty_nhwc(b, c_ * (len(ks) + 1), h, w, x.device)
         self.cv1(x, out=cat[:, :c_])
-        prev_k, prev = 1, cat[:, :c_]
-        for i, k in enumerate(ks):
-            dst = cat[:, (i + 1) * c_:(i + 2) * c_]
-            step = k - prev_k + 1            # pool_k = pool_step(pool_prev) for stride-1 max pools
-            if i > 0 and step >= 1 and step % 2 == 1 and k > prev_k:
-                ops.maxpool_s1(prev, dst, step)
-            else:
-                ops.maxpool_s1(cat[:, :c_], dst, k)
-            prev_k, prev = k, dst
+        steps = [ks[0]] + [ks[i] - ks[i - 1] + 1 for i in range(1, len(ks))]    # pool_k = pool_step(pool_prev)
+        if len(ks) == 3 and all(st >= 1 and st % 2 == 1 for st in steps) and c_ % 16 == 0 and h * w * 64 <= 200 * 1024:
+            ops.maxpool_cascade3(cat[:, :c_], cat, [c_, 2 * c_, 3 * c_], steps)       # one smem-staged pass
+        else:
+            prev_k, prev = 1, cat[:, :c_]
+            for i, k in enumerate(ks):
+                dst = cat[:, (i + 1) * c_:(i + 2) * c_]
+                step = k - prev_k + 1
+                if i > 0 and step >= 1 and step % 2 == 1 and k > prev_k:
+                    ops.maxpool_s1(prev, dst, step)
+                else:
+                    ops.maxpool_s1(cat[:, :c_], dst, k)
+                prev_k, prev = k, dst
         return self.cv2(cat, out=out)
 
 

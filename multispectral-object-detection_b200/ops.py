@@ -18,7 +18,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, DT_BF16, DT_F32, ConvArgs
 
 __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "empty_nhwc", "to_nhwc_bf16", "conv2d", "gemm", "focus_gather",
-    "maxpool_s1", "upsample2x", "add", "copy_into", "gpt_pool_tokens", "layernorm", "attention",
+    "maxpool_s1", "maxpool_cascade3", "upsample2x", "add", "copy_into", "gpt_pool_tokens", "layernorm", "attention",
     "gpt_unpool", "detect_decode", "pack_conv_weight", "pack_linear_weight",
 ]
 
@@ -187,6 +187,18 @@ def maxpool_s1(x: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
     b, c, h, w = x.shape
     _lib.check(lib.cft_maxpool_s1(xp, ldx, 0, yp, ldy, 0, b, h, w, c, k, _stream()), "cft_maxpool_s1")
     return out
+
+
+def maxpool_cascade3(x: torch.Tensor, cat: torch.Tensor, coffs, ks) -> torch.Tensor:
+    """Three stride-1 max pools in cascade (windows ks) of ``x``; stage i is written to channels
+    [coffs[i], coffs[i]+C) of ``cat`` (x may itself be a slice of ``cat``)."""
+    lib = _lib.lib()
+    xp, ldx = nhwc_desc(x)
+    yp, ldy = nhwc_desc(cat)
+    b, c, h, w = x.shape
+    _lib.check(lib.cft_maxpool_cascade3(xp, ldx, 0, yp, ldy, coffs[0], coffs[1], coffs[2], b, h, w, c,
+                                        ks[0], ks[1], ks[2], _stream()), "cft_maxpool_cascade3")
+    return cat
 
 
 def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

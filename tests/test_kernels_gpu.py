@@ -153,6 +153,21 @@ def test_maxpool_cascade_equals_5_9_13(cft):
     assert torch.equal(cat[:, :64], x)
 
 
+@pytest.mark.parametrize("H,W,C", [(20, 20, 512), (32, 40, 64), (7, 5, 16)])
+def test_maxpool_cascade3_is_spp(H, W, C, cft):
+    """One-pass SPP pools: cascade (5,5,5) == max_pool2d k=5,9,13 (models/common.py:160-165), bit-exact."""
+    ops = cft.ops
+    x = nhwc(rnd(2, C, H, W, seed=4))
+    cat = torch.zeros((2, 4 * C, H, W), device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ops.copy_into(x, cat[:, :C])
+    ops.maxpool_cascade3(cat[:, :C], cat, [C, 2 * C, 3 * C], [5, 5, 5])
+    torch.cuda.synchronize()
+    xf = x.float()
+    assert torch.equal(cat[:, :C], x)
+    for i, k in enumerate((5, 9, 13)):
+        assert torch.equal(cat[:, C * (i + 1):C * (i + 2)].float(), F.max_pool2d(xf, k, 1, k // 2)), k
+
+
 def test_upsample_add_copy(cft):
     ops = cft.ops
     a, b = nhwc(rnd(2, 64, 10, 12, seed=1)), nhwc(rnd(2, 64, 10, 12, seed=2))
