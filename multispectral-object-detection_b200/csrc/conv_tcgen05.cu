@@ -34,9 +34,9 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 192 * 1024;   // operand ring
+constexpr int kSmemBudget = 160 * 1024;   // operand ring
 constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
-constexpr int kNumStageC = 2;
+constexpr int kNumStageC = 4;            // 2 column groups x 2 (double-buffered)
 constexpr int kTailBytes = 256 + 1024;     // barriers + TMEM slot, bias staging
 
 struct __align__(64) TensorMaps {
@@ -49,7 +49,8 @@ struct __align__(64) TensorMaps {
 struct ConvParams {
   int B, Ho, Wo, Cout;
   int taps, kchunks, stride;
-  int kelems, layout;       // K elements per ring stage (16 / 32 / 64) and the matching UMMA swizzle code
+  int kelems, layout;       // K elements per unit (16 / 32 / 64) and the matching UMMA swizzle code
+  int ups;                  // K units (taps) per ring stage
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
   int m_tiles;              // spatial tiles = B * tiles_y * tiles_x; num_tiles counts (pairs of) m-tiles x n-blocks
@@ -139,52 +140,63 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int k_iters = p.taps * p.kchunks;
+  // K is walked in units of (tap, kelems-wide channel chunk); a ring stage holds p.ups consecutive units
+  // (several taps per stage when the channel count is small, so that per-stage barrier traffic is amortised).
+  const int k_units = p.taps * p.kchunks;
+  const int k_iters = (k_units + p.ups - 1) / p.ups;
   const uint32_t row_bytes = static_cast<uint32_t>(p.kelems) * 2u;   // operand tile row: 32 / 64 / 128 B
+  const uint32_t a_unit_bytes = 128u * row_bytes;                     // one unit's A tile (128 pixel rows)
+  const uint32_t b_unit_bytes = static_cast<uint32_t>(b_rows) * row_bytes;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(p.TW * p.TH + b_rows) * row_bytes;   // per CTA
+    const uint32_t tx_unit = static_cast<uint32_t>(p.TW * p.TH + b_rows) * row_bytes;   // per CTA, per unit
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
-      for (int tap = 0; tap < p.taps; ++tap) {
-        int mi = 0, dy = 0, dx = 0;
-        if (p.taps == 9) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          if (p.stride == 1) {
-            dy = ky - 1;
-            dx = kx - 1;
-          } else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
-            const int py = (ky != 1), px = (kx != 1);
-            dy = (ky == 0) ? -1 : 0;
-            dx = (kx == 0) ? -1 : 0;
-            mi = py * 2 + px;
+      for (int it = 0; it < k_iters; ++it) {
+        const int u0 = it * p.ups;
+        const int n_units = (k_units - u0) < p.ups ? (k_units - u0) : p.ups;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one_sync()) {
+          if constexpr (kCtas == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_unit * n_units);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], tx_unit * n_units);
           }
-        }
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (elect_one_sync()) {
+          for (int j = 0; j < n_units; ++j) {
+            const int u = u0 + j;
+            const int tap = u / p.kchunks, kc = u - tap * p.kchunks;
+            int mi = 0, dy = 0, dx = 0;
+            if (p.taps == 9) {
+              const int ky = tap / 3, kx = tap - 3 * ky;
+              if (p.stride == 1) {
+                dy = ky - 1;
+                dx = kx - 1;
+              } else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
+                const int py = (ky != 1), px = (kx != 1);
+                dy = (ky == 0) ? -1 : 0;
+                dx = (kx == 0) ? -1 : 0;
+                mi = py * 2 + px;
+              }
+            }
+            uint8_t* sa = smem_a + stage * kATileBytes + j * a_unit_bytes;
+            uint8_t* sb = smem_b + stage * b_stage_bytes + j * b_unit_bytes;
             if constexpr (kCtas == 2) {
-              tma_load_4d_2sm(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
-                              t.y0 + dy, t.b);
-              tma_load_3d_2sm(smem_b + stage * b_stage_bytes, &maps.b, &full_bar[stage], kc * p.kelems, tap,
-                              t.n0 + rank * b_rows);
-              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_bytes);
-              else mbar_arrive_cluster(&full_bar[stage], 0);
+              tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
+              tma_load_3d_2sm(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0 + rank * b_rows);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_4d(smem_a + stage * kATileBytes, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx,
-                          t.y0 + dy, t.b);
-              tma_load_3d(smem_b + stage * b_stage_bytes, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
+              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
+              tma_load_3d(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
             }
           }
-          __syncwarp();
-          if (++stage == stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
@@ -208,12 +220,17 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
-          for (int k = 0; k < ksteps; ++k) {          // +32 B along K inside the swizzle atom = +2 in the address field
-            const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
-            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
-            if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          const int u0 = it * p.ups;
+          const int n_units = (k_units - u0) < p.ups ? (k_units - u0) : p.ups;
+          for (int j = 0; j < n_units; ++j) {
+            const uint32_t a_lo = a_lo0 + stage * a_lo_stride + j * (a_unit_bytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * b_lo_stride + j * (b_unit_bytes >> 4);
+            for (int k = 0; k < ksteps; ++k) {        // +32 B along K inside the swizzle atom = +2 in the address field
+              const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
+              const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
+              if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | j | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc, (it | j | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (kCtas == 2) {
             umma_commit_2sm(&empty_bar[stage]);                       // frees the slot in both CTAs
@@ -239,7 +256,8 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;         // accumulator row = pixel within the tile
     const int gtid = (ew & 3) * 32 + lane; // thread index within the group
-    uint8_t* stage_c = smem_c + grp * kStageCBytes;
+    uint8_t* stage_c0 = smem_c + grp * 2 * kStageCBytes;   // this group's two staging buffers
+    uint32_t sbuf = 0;
     uint64_t* rbar = &res_bar[grp];
     uint32_t res_phase = 0;
     int acc = 0;
@@ -260,9 +278,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       bool waited_full = false;
       for (int sg = c_begin; sg < c_end; sg += cps) {
         const int nch = (c_end - sg) < cps ? (c_end - sg) : cps;
-        // acquire the staging buffer: earlier stores out of it have been read; prefetch the residual tile
+        // acquire a staging buffer: the store issued out of it two sub-groups ago has been read (the most
+        // recent store may still be in flight out of the other buffer); prefetch the residual tile into it
+        uint8_t* stage_c = stage_c0 + sbuf * kStageCBytes;
+        sbuf ^= 1u;
         if (gtid == 0) {
-          bulk_wait_read<0>();
+          bulk_wait_read<1>();
           if (use_res) {
             mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
             for (int i = 0; i < nch; ++i)
@@ -480,18 +501,23 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.kelems = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
   p.layout = p.kelems == 64 ? 2 : (p.kelems == 32 ? 4 : 6);   // UMMA LayoutType: SW128 / SW64 / SW32
   p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
+  p.ups = (p.kchunks == 1 && p.taps > 1) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
   p.stride = s;
   pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   p.block_n = pick_block_n(a->Cout);
-  p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
   const long long m_tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y;
+  // too few tiles to fill the GPU (the M = 4096 GEMMs of the CFT blocks): trade tile width for parallelism
+  while (m_tiles * ((a->Cout + p.block_n - 1) / p.block_n) < sm_count() && p.block_n >= 128 && (p.block_n / 2) % 32 == 0 &&
+         a->Cout % (p.block_n / 2) == 0)
+    p.block_n /= 2;
+  p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
   CFT_REQUIRE(m_tiles * p.n_blocks < (1LL << 31), "cft_conv2d: too many tiles");
   p.m_tiles = static_cast<int>(m_tiles);
   // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem
   // traffic per MMA -- worth it once the layer is tensor-bound (enough K work per tile) and has >= 2 tiles.
-  const int k_iters = p.taps * p.kchunks;
+  const int k_iters = (p.taps * p.kchunks + p.ups - 1) / p.ups;
   int ctas = (g_force_ctas == 1) ? 1 : 2;
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
