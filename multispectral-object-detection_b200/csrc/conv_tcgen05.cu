@@ -34,9 +34,9 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 160 * 1024;   // operand ring
+constexpr int kSmemTotal = 227 * 1024;    // dynamic smem per CTA on sm_100
 constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
-constexpr int kNumStageC = 4;            // 2 column groups x 2 (double-buffered)
+constexpr int kMaxStageC = 4;            // 2 column groups x up to 2 buffers
 constexpr int kTailBytes = 256 + 1024;     // barriers + TMEM slot, bias staging
 
 struct __align__(64) TensorMaps {
@@ -51,6 +51,8 @@ struct ConvParams {
   int taps, kchunks, stride;
   int kelems, layout;       // K elements per unit (16 / 32 / 64) and the matching UMMA swizzle code
   int ups;                  // K units (taps) per ring stage
+  int cbufs;                // epilogue staging buffers per column group (1 or 2)
+  int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
   int m_tiles;              // spatial tiles = B * tiles_y * tiles_x; num_tiles counts (pairs of) m-tiles x n-blocks
@@ -105,7 +107,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * kATileBytes;
   uint8_t* smem_c = smem_b + stages * b_stage_bytes;  // b_stage_bytes is a multiple of 2048 -> 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kNumStageC * kStageCBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * p.cbufs * kStageCBytes);
   uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2] MMA -> epilogue
@@ -256,7 +258,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;         // accumulator row = pixel within the tile
     const int gtid = (ew & 3) * 32 + lane; // thread index within the group
-    uint8_t* stage_c0 = smem_c + grp * 2 * kStageCBytes;   // this group's two staging buffers
+    uint8_t* stage_c0 = smem_c + grp * p.cbufs * kStageCBytes;   // this group's staging buffer(s)
     uint32_t sbuf = 0;
     uint64_t* rbar = &res_bar[grp];
     uint32_t res_phase = 0;
@@ -281,9 +283,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         // acquire a staging buffer: the store issued out of it two sub-groups ago has been read (the most
         // recent store may still be in flight out of the other buffer); prefetch the residual tile into it
         uint8_t* stage_c = stage_c0 + sbuf * kStageCBytes;
-        sbuf ^= 1u;
+        if (p.cbufs == 2) sbuf ^= 1u;
         if (gtid == 0) {
-          bulk_wait_read<1>();
+          if (p.cbufs == 2) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
           if (use_res) {
             mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
             for (int i = 0; i < nch; ++i)
@@ -362,7 +365,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(bar_id, 128);
-        if (gtid == 0) {
+        if (gtid == 0 && !p.dbg_skip_store) {
           for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
             tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
           bulk_commit();
@@ -467,6 +470,8 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
+const int g_cbufs = (getenv("CFT_STAGE_BUFS") && atoi(getenv("CFT_STAGE_BUFS")) == 2) ? 2 : 1;   // epilogue staging depth
+const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
 }  // namespace
@@ -501,7 +506,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.kelems = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
   p.layout = p.kelems == 64 ? 2 : (p.kelems == 32 ? 4 : 6);   // UMMA LayoutType: SW128 / SW64 / SW32
   p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
-  p.ups = (p.kchunks == 1 && p.taps > 1) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
+  p.ups = (p.kchunks == 1 && p.taps > 1 && !g_ups_off) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
   p.stride = s;
   pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
@@ -509,8 +514,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.block_n = pick_block_n(a->Cout);
   const long long m_tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y;
   // too few tiles to fill the GPU (the M = 4096 GEMMs of the CFT blocks): trade tile width for parallelism
-  while (m_tiles * ((a->Cout + p.block_n - 1) / p.block_n) < sm_count() && p.block_n >= 128 && (p.block_n / 2) % 32 == 0 &&
-         a->Cout % (p.block_n / 2) == 0)
+  while (a->Cin * p.taps <= 1024 && 2 * m_tiles * ((a->Cout + p.block_n - 1) / p.block_n) <= sm_count() &&
+         p.block_n >= 128 && (p.block_n / 2) % 32 == 0 && a->Cout % (p.block_n / 2) == 0)
     p.block_n /= 2;
   p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
   CFT_REQUIRE(m_tiles * p.n_blocks < (1LL << 31), "cft_conv2d: too many tiles");
@@ -522,8 +527,11 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
   p.num_tiles = static_cast<int>(((m_tiles + ctas - 1) / ctas) * p.n_blocks);
+  p.cbufs = g_cbufs;
+  p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
+  const int ring_budget = kSmemTotal - 1024 - kTailBytes - 2 * p.cbufs * kStageCBytes;
   const int stage_bytes = kATileBytes + (p.block_n / ctas) * 128;
-  p.stages = kSmemBudget / stage_bytes;
+  p.stages = ring_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.act = a->act;
   p.out_f32 = a->out_dtype == CFT_DT_F32;
@@ -591,9 +599,9 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     }
   }
 
-  const int smem_bytes = 1024 + p.stages * stage_bytes + kNumStageC * kStageCBytes + kTailBytes;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + 2 * p.cbufs * kStageCBytes + kTailBytes;
   if (!g_attr_set) {
-    const int max_smem = 1024 + kSmemBudget + kNumStageC * kStageCBytes + kTailBytes;
+    const int max_smem = kSmemTotal;
     rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
                     "cudaFuncSetAttribute(conv_tcgen05<1>)");
     if (rc) return rc;

@@ -35,6 +35,7 @@ SHAPES = [
 def main():
     timed = "--time" in sys.argv
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    act = 0 if "--noact" in sys.argv else 1
     peaks_t, peaks_b = 1385.4e12, 6584.8e9
     for name, cin, cout, h, w, k, s in SHAPES:
         if only and name not in only:
@@ -43,7 +44,7 @@ def main():
         x = torch.randn(b, cin, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         wt = torch.randn(cout, cin, k, k) / math.sqrt(cin * k * k)
         wp, bp = ops.pack_conv_weight(wt, torch.zeros(cout), None, device=DEV)
-        y = ops.conv2d(x, wp, bp, k, s, 1, cout=cout)            # warm-up
+        y = ops.conv2d(x, wp, bp, k, s, act, cout=cout)            # warm-up
         torch.cuda.synchronize()
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -52,7 +53,7 @@ def main():
             for _ in range(5):
                 flush.zero_()                                     # L2 flush between timed iterations
                 e0.record()
-                ops.conv2d(x, wp, bp, k, s, 1, out=y, cout=cout)
+                ops.conv2d(x, wp, bp, k, s, act, out=y, cout=cout)
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
@@ -63,7 +64,7 @@ def main():
             print(f"{name:28s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s ({flops/ms/1e9*1e12/peaks_t*100:5.1f}% tensor)  "
                   f"{byts/ms/1e6:8.1f} GB/s ({byts/ms/1e6*1e9/peaks_b*100:5.1f}% hbm)  AI {flops/byts:6.0f}", flush=True)
         else:
-            ops.conv2d(x, wp, bp, k, s, 1, out=y, cout=cout)
+            ops.conv2d(x, wp, bp, k, s, act, out=y, cout=cout)
             torch.cuda.synchronize()
 
 
