@@ -44,6 +44,13 @@ __device__ __forceinline__ float silu_fast(float v) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return v * r;
 }
+// SiLU with ONE SFU op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32: abs error ~5e-4 -> |err| <= |x| * 2.5e-4).
+__device__ __forceinline__ float silu_tanh(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == CFT_ACT_SILU) return silu_f(v);

@@ -157,48 +157,80 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const uint32_t tx_unit = static_cast<uint32_t>(p.TW * p.TH + b_rows) * row_bytes;   // per CTA, per unit
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
-      for (int it = 0; it < k_iters; ++it) {
-        const int u0 = it * p.ups;
-        const int n_units = (k_units - u0) < p.ups ? (k_units - u0) : p.ups;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (elect_one_sync()) {
-          if constexpr (kCtas == 2) {
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_unit * n_units);
-            else mbar_arrive_cluster(&full_bar[stage], 0);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], tx_unit * n_units);
+      auto tap_offsets = [&](int tap, int& mi, int& dy, int& dx) {
+        mi = 0; dy = 0; dx = 0;
+        if (p.taps == 9) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          if (p.stride == 1) {
+            dy = ky - 1;
+            dx = kx - 1;
+          } else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
+            const int py = (ky != 1), px = (kx != 1);
+            dy = (ky == 0) ? -1 : 0;
+            dx = (kx == 0) ? -1 : 0;
+            mi = py * 2 + px;
           }
-          for (int j = 0; j < n_units; ++j) {
-            const int u = u0 + j;
-            const int tap = u / p.kchunks, kc = u - tap * p.kchunks;
-            int mi = 0, dy = 0, dx = 0;
-            if (p.taps == 9) {
-              const int ky = tap / 3, kx = tap - 3 * ky;
-              if (p.stride == 1) {
-                dy = ky - 1;
-                dx = kx - 1;
-              } else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
-                const int py = (ky != 1), px = (kx != 1);
-                dy = (ky == 0) ? -1 : 0;
-                dx = (kx == 0) ? -1 : 0;
-                mi = py * 2 + px;
+        }
+      };
+      if (p.ups == 1) {
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int mi, dy, dx;
+          tap_offsets(tap, mi, dy, dx);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (elect_one_sync()) {
+              uint8_t* sa = smem_a + stage * kATileBytes;
+              uint8_t* sb = smem_b + stage * b_stage_bytes;
+              if constexpr (kCtas == 2) {
+                tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
+                tma_load_3d_2sm(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0 + rank * b_rows);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_unit);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], tx_unit);
+                tma_load_4d(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
+                tma_load_3d(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
               }
             }
-            uint8_t* sa = smem_a + stage * kATileBytes + j * a_unit_bytes;
-            uint8_t* sb = smem_b + stage * b_stage_bytes + j * b_unit_bytes;
-            if constexpr (kCtas == 2) {
-              tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
-              tma_load_3d_2sm(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0 + rank * b_rows);
-            } else {
-              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
-              tma_load_3d(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
+            __syncwarp();
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
         }
-        __syncwarp();
-        if (++stage == stages) {
-          stage = 0;
-          phase ^= 1u;
+      } else {
+        for (int it = 0; it < k_iters; ++it) {            // kchunks == 1 here: a unit is a tap
+          const int u0 = it * p.ups;
+          const int n_units = (k_units - u0) < p.ups ? (k_units - u0) : p.ups;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (elect_one_sync()) {
+            if constexpr (kCtas == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_unit * n_units);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], tx_unit * n_units);
+            }
+            for (int j = 0; j < n_units; ++j) {
+              const int tap = u0 + j;
+              int mi, dy, dx;
+              tap_offsets(tap, mi, dy, dx);
+              uint8_t* sa = smem_a + stage * kATileBytes + j * a_unit_bytes;
+              uint8_t* sb = smem_b + stage * b_stage_bytes + j * b_unit_bytes;
+              if constexpr (kCtas == 2) {
+                tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], 0, t.x0 + dx, t.y0 + dy, t.b);
+                tma_load_3d_2sm(sb, &maps.b, &full_bar[stage], 0, tap, t.n0 + rank * b_rows);
+              } else {
+                tma_load_4d(sa, &maps.a[mi], &full_bar[stage], 0, t.x0 + dx, t.y0 + dy, t.b);
+                tma_load_3d(sb, &maps.b, &full_bar[stage], 0, tap, t.n0);
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -222,16 +254,27 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          const int u0 = it * p.ups;
-          const int n_units = (k_units - u0) < p.ups ? (k_units - u0) : p.ups;
-          for (int j = 0; j < n_units; ++j) {
-            const uint32_t a_lo = a_lo0 + stage * a_lo_stride + j * (a_unit_bytes >> 4);
-            const uint32_t b_lo = b_lo0 + stage * b_lo_stride + j * (b_unit_bytes >> 4);
-            for (int k = 0; k < ksteps; ++k) {        // +32 B along K inside the swizzle atom = +2 in the address field
+          if (p.kelems == 64) {     // one (tap, 64-channel) unit per stage: 4 back-to-back MMAs, no inner loops
+            const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {             // +32 B along K inside the swizzle atom = +2 in the address field
               const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
               const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
-              if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | j | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, da, db, idesc, (it | j | k) != 0 ? 1u : 0u);
+              if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          } else {                  // small-Cin convs: several 16/32-element units (taps) per stage
+            const int u0 = it * p.ups;
+            const int n_units = (k_units - u0) < p.ups ? (k_units - u0) : p.ups;
+            for (int j = 0; j < n_units; ++j) {
+              const uint32_t a_lo = a_lo0 + stage * a_lo_stride + j * (a_unit_bytes >> 4);
+              const uint32_t b_lo = b_lo0 + stage * b_lo_stride + j * (b_unit_bytes >> 4);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
+                if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | j | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem, da, db, idesc, (it | j | k) != 0 ? 1u : 0u);
+              }
             }
           }
           if constexpr (kCtas == 2) {
@@ -333,6 +376,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           } else if (p.act == CFT_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+          } else if (p.act == 3) {     // experiment (CFT_SILU_TANH): one-SFU-op SiLU
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = silu_tanh(f[i]);
           }
           // staging tile = TMA box (32 channels x TW x TH), hardware-swizzled rows:
           //   bf16: 64 B rows, SWIZZLE_64B  (16 B chunk ^= (row >> 1) & 3)
@@ -471,6 +517,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const int g_cbufs = (getenv("CFT_STAGE_BUFS") && atoi(getenv("CFT_STAGE_BUFS")) == 2) ? 2 : 1;   // epilogue staging depth
+const bool g_silu_tanh = getenv("CFT_SILU_TANH") != nullptr;
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
@@ -533,7 +580,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   const int stage_bytes = kATileBytes + (p.block_n / ctas) * 128;
   p.stages = ring_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  p.act = a->act;
+  p.act = (a->act == CFT_ACT_SILU && g_silu_tanh) ? 3 : a->act;
   p.out_f32 = a->out_dtype == CFT_DT_F32;
   p.ldy = a->ldy;
   p.y_coff = a->y_coff;
