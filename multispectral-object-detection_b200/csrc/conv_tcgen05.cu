@@ -28,15 +28,16 @@ using namespace cft::ptx;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = one 128B swizzle row
-constexpr int kThreads = 384;          // TMA, MMA, TMEM-alloc, idle, 8 epilogue warps
-constexpr int kEpilogueWarps = 8;
+constexpr int kEpiGroups = 4;          // column groups of 4 warps (one warp per TMEM lane quarter) each
+constexpr int kEpilogueWarps = 4 * kEpiGroups;
+constexpr int kThreads = 128 + 32 * kEpilogueWarps;   // TMA, MMA, TMEM-alloc, idle + epilogue warps
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
 constexpr int kTmemCols = 512;
 constexpr int kSmemTotal = 227 * 1024;    // dynamic smem per CTA on sm_100
 constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
-constexpr int kMaxStageC = 4;            // 2 column groups x up to 2 buffers
+
 constexpr int kTailBytes = 256 + 1024;     // barriers + TMEM slot, bias staging
 
 struct __align__(64) TensorMaps {
@@ -51,7 +52,6 @@ struct ConvParams {
   int taps, kchunks, stride;
   int kelems, layout;       // K elements per unit (16 / 32 / 64) and the matching UMMA swizzle code
   int ups;                  // K units (taps) per ring stage
-  int cbufs;                // epilogue staging buffers per column group (1 or 2)
   int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
@@ -107,14 +107,14 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * kATileBytes;
   uint8_t* smem_c = smem_b + stages * b_stage_bytes;  // b_stage_bytes is a multiple of 2048 -> 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * p.cbufs * kStageCBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiGroups * kStageCBytes);
   uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2] MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2] epilogue -> MMA
-  uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2] residual TMA -> epilogue group
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);   // [256] bias of the current n-block
+  uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [kEpiGroups] residual TMA -> epilogue group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kEpiGroups);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6 + kEpiGroups);   // [256] bias of the current n-block
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -128,8 +128,8 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpilogueWarps * kCtas);   // one arrive per epilogue warp (of both CTAs)
-      mbar_init(&res_bar[i], 1);
     }
+    for (int i = 0; i < kEpiGroups; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -295,21 +295,19 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 2 column groups x 4 warps =====================
+    // ===================== epilogue: kEpiGroups column groups x 4 warps =====================
     const int ew = warp - 4;
-    const int grp = ew >> 2;               // which half of the N columns
+    const int grp = ew >> 2;               // column group: handles 32-column chunks grp, grp + kEpiGroups, ...
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;         // accumulator row = pixel within the tile
     const int gtid = (ew & 3) * 32 + lane; // thread index within the group
-    uint8_t* stage_c0 = smem_c + grp * p.cbufs * kStageCBytes;   // this group's staging buffer(s)
-    uint32_t sbuf = 0;
+    uint8_t* stage_c = smem_c + grp * kStageCBytes;   // this group's staging buffer
     uint64_t* rbar = &res_bar[grp];
     uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int chunks_total = (p.block_n + 31) >> 5;                  // 32-column chunks
-    const int c_begin = grp == 0 ? 0 : (chunks_total + 1) >> 1;
-    const int c_end = grp == 0 ? (chunks_total + 1) >> 1 : chunks_total;
+    const int my_chunks = chunks_total > grp ? (chunks_total - grp + kEpiGroups - 1) / kEpiGroups : 0;
     const int cps = p.out_f32 ? 1 : 2;                               // chunks per staging buffer (16 KiB)
     const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
     const uint32_t c_chunk_stride = 128u * c_row_bytes;
@@ -321,15 +319,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
       bool waited_full = false;
-      for (int sg = c_begin; sg < c_end; sg += cps) {
-        const int nch = (c_end - sg) < cps ? (c_end - sg) : cps;
+      for (int sg = 0; sg < my_chunks; sg += cps) {        // this group's chunks: grp + kEpiGroups * (sg + i)
+        const int nch = (my_chunks - sg) < cps ? (my_chunks - sg) : cps;
         // acquire a staging buffer: the store issued out of it two sub-groups ago has been read (the most
         // recent store may still be in flight out of the other buffer); prefetch the residual tile into it
-        uint8_t* stage_c = stage_c0 + sbuf * kStageCBytes;
-        if (p.cbufs == 2) sbuf ^= 1u;
         if (gtid == 0) {
-          if (p.cbufs == 2) bulk_wait_read<1>();
-          else bulk_wait_read<0>();
+          bulk_wait_read<0>();
           if (use_res) {
             mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
             for (int i = 0; i < nch; ++i)
@@ -337,9 +332,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           }
         }
         if (t.n0 != bias_n0) {          // (re)stage this n-block's bias; published by the barrier below
-          for (int i = gtid; i < (c_end - c_begin) * 32; i += 128) {
-            const int n = t.n0 + c_begin * 32 + i;
-            bias_s[c_begin * 32 + i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+          for (int i = gtid; i < my_chunks * 32; i += 128) {
+            const int col = (grp + kEpiGroups * (i >> 5)) * 32 + (i & 31);
+            const int n = t.n0 + col;
+            bias_s[col] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
           }
           bias_n0 = t.n0;
         }
@@ -354,7 +350,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           res_phase ^= 1u;
         }
         for (int ci = 0; ci < nch; ++ci) {
-          const int c0 = (sg + ci) * 32;
+          const int c0 = (grp + kEpiGroups * (sg + ci)) * 32;
           uint8_t* stage = stage_c + ci * c_chunk_stride;
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
@@ -376,7 +372,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           } else if (p.act == CFT_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
-          } else if (p.act == 3) {     // experiment (CFT_SILU_TANH): one-SFU-op SiLU
+          } else if (p.act == 3) {     // SiLU as h + h*tanh(h) (one SFU op per element)
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = silu_tanh(f[i]);
           }
@@ -413,7 +409,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         named_bar_sync(bar_id, 128);
         if (gtid == 0 && !p.dbg_skip_store) {
           for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
-            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
+            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (grp + kEpiGroups * (sg + i)) * 32, t.x0, t.y0, t.b);
           bulk_commit();
         }
       }
@@ -516,8 +512,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
-const int g_cbufs = (getenv("CFT_STAGE_BUFS") && atoi(getenv("CFT_STAGE_BUFS")) == 2) ? 2 : 1;   // epilogue staging depth
-const bool g_silu_tanh = getenv("CFT_SILU_TANH") != nullptr;
+const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
@@ -574,9 +569,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
   p.num_tiles = static_cast<int>(((m_tiles + ctas - 1) / ctas) * p.n_blocks);
-  p.cbufs = g_cbufs;
   p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
-  const int ring_budget = kSmemTotal - 1024 - kTailBytes - 2 * p.cbufs * kStageCBytes;
+  const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * kStageCBytes;
   const int stage_bytes = kATileBytes + (p.block_n / ctas) * 128;
   p.stages = ring_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -646,7 +640,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     }
   }
 
-  const int smem_bytes = 1024 + p.stages * stage_bytes + 2 * p.cbufs * kStageCBytes + kTailBytes;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + kEpiGroups * kStageCBytes + kTailBytes;
   if (!g_attr_set) {
     const int max_smem = kSmemTotal;
     rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
