@@ -12,9 +12,12 @@ using namespace cft;
 // ------------------------------------------------------------------ tokeniser
 // grid = (2*va*ha, B); block = 128 threads over 8-channel vectors.
 // Bin i covers rows [floor(i*H/va), ceil((i+1)*H/va)) -- torch AdaptiveAvgPool2d (models/common.py:578,608-609).
-__global__ void pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb,
-                                   const __nv_bfloat16* __restrict__ ir, int ld_ir, int H, int W, int C, int va,
-                                   int ha, const float* __restrict__ pos, float* __restrict__ tok) {
+__global__ void __launch_bounds__(256)
+pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb, const __nv_bfloat16* __restrict__ ir, int ld_ir,
+                   int H, int W, int C, int va, int ha, const float* __restrict__ pos, float* __restrict__ tok) {
+  // 256 threads = (C/8 channel vectors) x (pixel slices): every thread accumulates its slice of the bin, slices are
+  // combined through smem.  All 256 threads stay busy for any C (the per-token kernel used C/8 of 128 threads).
+  __shared__ float red[256 * 8];
   const int t = blockIdx.x, b = blockIdx.y;
   const int cells = va * ha, T = 2 * cells;
   const int mod = t / cells, cell = t - mod * cells;
@@ -23,20 +26,36 @@ __global__ void pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld
   const int x0 = (bj * W) / ha, x1 = ((bj + 1) * W + ha - 1) / ha;
   const __nv_bfloat16* src = mod == 0 ? rgb : ir;
   const int ld = mod == 0 ? ld_rgb : ld_ir;
-  const float inv = 1.0f / static_cast<float>((y1 - y0) * (x1 - x0));
-  for (int cv = threadIdx.x; cv < C / 8; cv += blockDim.x) {
+  const int bw = x1 - x0, npix = (y1 - y0) * bw;
+  const float inv = 1.0f / static_cast<float>(npix);
+  const int nvec = C / 8;
+  for (int v0 = 0; v0 < nvec; v0 += 256) {              // C <= 2048: one pass
+    const int nv = min(nvec - v0, 256);
+    const int slices = 256 / nv > 0 ? 256 / nv : 1;
+    const int cv = threadIdx.x % nv, sl = threadIdx.x / nv;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) {
+    if (sl < slices) {
+      for (int p = sl; p < npix; p += slices) {
+        const int y = y0 + p / bw, x = x0 + p % bw;
         float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(src + ((static_cast<long long>(b) * H + y) * W + x) * ld + cv * 8), f);
+        unpack8(*reinterpret_cast<const bf16x8*>(src + ((static_cast<long long>(b) * H + y) * W + x) * ld + (v0 + cv) * 8), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += f[i];
       }
-    float* o = tok + (static_cast<long long>(b) * T + t) * C + cv * 8;
-    const float* pe = pos + static_cast<long long>(t) * C + cv * 8;
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = s[i] * inv + pe[i];
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = s[i];
+    __syncthreads();
+    if (sl == 0 && threadIdx.x < nv) {
+      for (int q = 1; q < slices; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += red[(q * nv + cv) * 8 + i];
+      float* o = tok + (static_cast<long long>(b) * T + t) * C + (v0 + cv) * 8;
+      const float* pe = pos + static_cast<long long>(t) * C + (v0 + cv) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = s[i] * inv + pe[i];
+    }
+    __syncthreads();
   }
 }
 
@@ -44,40 +63,54 @@ __global__ void pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld
 template <bool kOutF32>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                  const float* __restrict__ be, float eps, long long rows, int C, void* __restrict__ y) {
+  // one warp per row; the row is read from global memory once and kept in registers (C <= 2048)
+  constexpr int kMaxV = 16;                       // float4 per lane (C <= 2048)
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * C);
   const int n4 = C / 4;
+  float4 v[kMaxV];
   float s = 0.f;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = xr[i];
-    s += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < n4) {
+      v[j] = xr[i];
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / static_cast<float>(C);
   float q = 0.f;
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = xr[i];
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < n4) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
   const float4* g4 = reinterpret_cast<const float4*>(g);
   const float4* b4 = reinterpret_cast<const float4*>(be);
-  for (int i = lane; i < n4; i += 32) {
-    const float4 v = xr[i], gg = g4[i], bb = b4[i];
-    const float o0 = (v.x - mean) * rstd * gg.x + bb.x, o1 = (v.y - mean) * rstd * gg.y + bb.y;
-    const float o2 = (v.z - mean) * rstd * gg.z + bb.z, o3 = (v.w - mean) * rstd * gg.w + bb.w;
-    if constexpr (kOutF32) {
-      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * C)[i] = make_float4(o0, o1, o2, o3);
-    } else {
-      __nv_bfloat162* yo = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C) + 2 * i;
-      yo[0] = __floats2bfloat162_rn(o0, o1);
-      yo[1] = __floats2bfloat162_rn(o2, o3);
+#pragma unroll
+  for (int j = 0; j < kMaxV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < n4) {
+      const float4 gg = g4[i], bb = b4[i];
+      const float o0 = (v[j].x - mean) * rstd * gg.x + bb.x, o1 = (v[j].y - mean) * rstd * gg.y + bb.y;
+      const float o2 = (v[j].z - mean) * rstd * gg.z + bb.z, o3 = (v[j].w - mean) * rstd * gg.w + bb.w;
+      if constexpr (kOutF32) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * C)[i] = make_float4(o0, o1, o2, o3);
+      } else {
+        __nv_bfloat162* yo = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C) + 2 * i;
+        yo[0] = __floats2bfloat162_rn(o0, o1);
+        yo[1] = __floats2bfloat162_rn(o2, o3);
+      }
     }
   }
 }
@@ -368,7 +401,7 @@ extern "C" int cft_gpt_pool_tokens(const void* rgb, int ld_rgb, int coff_rgb, co
   CFT_REQUIRE(B > 0 && H >= 1 && W >= 1 && va >= 1 && ha >= 1 && B <= 65535, "cft_gpt_pool_tokens: bad shape");
   dim3 grid(2 * va * ha, B);
   LaunchScope ls(CFT_K_POOL_TOKENS, stream);
-  pool_tokens_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(rgb) + coff_rgb, ld_rgb,
+  pool_tokens_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(rgb) + coff_rgb, ld_rgb,
                                                reinterpret_cast<const __nv_bfloat16*>(ir) + coff_ir, ld_ir, H, W, C, va,
                                                ha, pos_emb, tokens);
   return ls.finish("cft_gpt_pool_tokens launch");
@@ -378,8 +411,8 @@ extern "C" int cft_layernorm(const float* x, const float* gamma, const float* be
                              void* y, int out_dtype, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   CFT_REQUIRE(x && gamma && beta && y, "cft_layernorm: null pointer");
-  CFT_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, "cft_layernorm: C must be a multiple of 4");
-  const int warps = 8;
+  CFT_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 2048, "cft_layernorm: C must be a multiple of 4, <= 2048");
+  const int warps = 4;
   const long long blocks = (rows + warps - 1) / warps;
   LaunchScope ls(CFT_K_LAYERNORM, stream);
   if (out_dtype == CFT_DT_F32)
