@@ -52,6 +52,9 @@ struct ConvParams {
   int taps, kchunks, stride;
   int kelems, layout;       // K elements per unit (16 / 32 / 64) and the matching UMMA swizzle code
   int ups;                  // K units (taps) per ring stage
+  int halo;                 // 3x3 s1 'row-reuse' mode: a stage = one filter column kx; the three ky taps are
+                            // 8-row-group offsets into one (TH+2) x TW pixel box (TW = 8)
+  int a_slot, b_slot;       // ring slot sizes in bytes
   int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
@@ -103,9 +106,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const int work0 = kCtas == 2 ? (blockIdx.x >> 1) : blockIdx.x;
   const int work_stride = kCtas == 2 ? (gridDim.x >> 1) : gridDim.x;
   const int b_rows = p.block_n / kCtas;                                     // weight rows this CTA stages
-  const uint32_t b_stage_bytes = static_cast<uint32_t>(b_rows) * 128u;      // ring slot size (>= bytes actually loaded)
+  const uint32_t a_stage_bytes = static_cast<uint32_t>(p.a_slot);           // ring slot sizes (>= bytes loaded)
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.b_slot);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + stages * kATileBytes;
+  uint8_t* smem_b = smem + stages * a_stage_bytes;
   uint8_t* smem_c = smem_b + stages * b_stage_bytes;  // b_stage_bytes is a multiple of 2048 -> 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiGroups * kStageCBytes);
   uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
@@ -145,7 +149,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   // K is walked in units of (tap, kelems-wide channel chunk); a ring stage holds p.ups consecutive units
   // (several taps per stage when the channel count is small, so that per-stage barrier traffic is amortised).
   const int k_units = p.taps * p.kchunks;
-  const int k_iters = (k_units + p.ups - 1) / p.ups;
+  const int k_iters = p.halo ? 3 * p.kchunks : (k_units + p.ups - 1) / p.ups;
   const uint32_t row_bytes = static_cast<uint32_t>(p.kelems) * 2u;   // operand tile row: 32 / 64 / 128 B
   const uint32_t a_unit_bytes = 128u * row_bytes;                     // one unit's A tile (128 pixel rows)
   const uint32_t b_unit_bytes = static_cast<uint32_t>(b_rows) * row_bytes;
@@ -172,14 +176,44 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           }
         }
       };
-      if (p.ups == 1) {
+      if (p.halo) {
+        // stage = (filter column kx, 64-channel chunk): ONE (TH+2) x TW pixel box serves the three taps ky = 0..2
+        const uint32_t tx_halo = static_cast<uint32_t>((p.TH + 2) * p.TW + 3 * b_rows) * 128u;
+        for (int kx = 0; kx < 3; ++kx) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (elect_one_sync()) {
+              uint8_t* sa = smem_a + stage * a_stage_bytes;
+              uint8_t* sb = smem_b + stage * b_stage_bytes;
+              if constexpr (kCtas == 2) {
+                tma_load_4d_2sm(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + kx - 1, t.y0 - 1, t.b);
+                for (int ky = 0; ky < 3; ++ky)
+                  tma_load_3d_2sm(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * 3 + kx,
+                                  t.n0 + rank * b_rows);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_halo);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], tx_halo);
+                tma_load_4d(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + kx - 1, t.y0 - 1, t.b);
+                for (int ky = 0; ky < 3; ++ky)
+                  tma_load_3d(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * 3 + kx, t.n0);
+              }
+            }
+            __syncwarp();
+            if (++stage == stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      } else if (p.ups == 1) {
         for (int tap = 0; tap < p.taps; ++tap) {
           int mi, dy, dx;
           tap_offsets(tap, mi, dy, dx);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             if (elect_one_sync()) {
-              uint8_t* sa = smem_a + stage * kATileBytes;
+              uint8_t* sa = smem_a + stage * a_stage_bytes;
               uint8_t* sb = smem_b + stage * b_stage_bytes;
               if constexpr (kCtas == 2) {
                 tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
@@ -215,7 +249,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
               const int tap = u0 + j;
               int mi, dy, dx;
               tap_offsets(tap, mi, dy, dx);
-              uint8_t* sa = smem_a + stage * kATileBytes + j * a_unit_bytes;
+              uint8_t* sa = smem_a + stage * a_stage_bytes + j * a_unit_bytes;
               uint8_t* sb = smem_b + stage * b_stage_bytes + j * b_unit_bytes;
               if constexpr (kCtas == 2) {
                 tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], 0, t.x0 + dx, t.y0 + dy, t.b);
@@ -244,7 +278,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     // smem operand descriptor: [0,14) start >> 4 | [32,46) SBO >> 4 | bit 46 version | [61,64) swizzle code
     const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (static_cast<uint32_t>(p.layout) << 29);
     const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
-    const uint32_t a_lo_stride = kATileBytes >> 4, b_lo_stride = b_stage_bytes >> 4;
+    const uint32_t a_lo_stride = a_stage_bytes >> 4, b_lo_stride = b_stage_bytes >> 4;
     const int ksteps = p.kelems / 16;
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -254,7 +288,20 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          if (p.kelems == 64) {     // one (tap, 64-channel) unit per stage: 4 back-to-back MMAs, no inner loops
+          if (p.halo) {             // 3 taps (ky) x 4 K-steps out of one pixel box: tap ky starts TW(=8) rows = 1024 B further
+            const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
+            const uint32_t b_tap = static_cast<uint32_t>(b_rows) * 128u >> 4;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + ky * 64 + 2 * k);
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + ky * b_tap + 2 * k);
+                if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | ky | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem, da, db, idesc, (it | ky | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else if (p.kelems == 64) {     // one (tap, 64-channel) unit per stage: 4 back-to-back MMAs, no inner loops
             const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {             // +32 B along K inside the swizzle atom = +2 in the address field
@@ -321,14 +368,14 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       bool waited_full = false;
       for (int sg = 0; sg < my_chunks; sg += cps) {        // this group's chunks: grp + kEpiGroups * (sg + i)
         const int nch = (my_chunks - sg) < cps ? (my_chunks - sg) : cps;
-        // acquire a staging buffer: the store issued out of it two sub-groups ago has been read (the most
-        // recent store may still be in flight out of the other buffer); prefetch the residual tile into it
+        // acquire the group's staging buffer (its previous store has been read out); prefetch the residual tile
         if (gtid == 0) {
           bulk_wait_read<0>();
           if (use_res) {
             mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
             for (int i = 0; i < nch; ++i)
-              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (sg + i) * 32, t.x0, t.y0, t.b);
+              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (grp + kEpiGroups * (sg + i)) * 32, t.x0,
+                          t.y0, t.b);
           }
         }
         if (t.n0 != bias_n0) {          // (re)stage this n-block's bias; published by the barrier below
@@ -513,6 +560,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
+const bool g_no_halo = getenv("CFT_NO_ROW_REUSE") != nullptr;
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
@@ -550,7 +598,15 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
   p.ups = (p.kchunks == 1 && p.taps > 1 && !g_ups_off) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
   p.stride = s;
-  pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
+  // row-reuse mode for L2-bound 3x3 stride-1 layers (measured L2->SM ceiling ~60 B/cycle/SM): 8 x 16 pixel tiles,
+  // the 3 vertical taps share one (16+2) x 8 pixel box -> 2.7x less activation traffic than 9 separate boxes
+  p.halo = (!g_no_halo && a->k == 3 && s == 1 && p.kelems == 64 && p.Wo % 8 == 0 && p.Ho % 16 == 0) ? 1 : 0;
+  if (p.halo) {
+    p.TW = 8;
+    p.TH = 16;
+  } else {
+    pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
+  }
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   p.block_n = pick_block_n(a->Cout);
@@ -564,14 +620,16 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.m_tiles = static_cast<int>(m_tiles);
   // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem
   // traffic per MMA -- worth it once the layer is tensor-bound (enough K work per tile) and has >= 2 tiles.
-  const int k_iters = (p.taps * p.kchunks + p.ups - 1) / p.ups;
+  const int k_iters = p.halo ? 3 * p.kchunks : (p.taps * p.kchunks + p.ups - 1) / p.ups;
   int ctas = (g_force_ctas == 1) ? 1 : 2;
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
   p.num_tiles = static_cast<int>(((m_tiles + ctas - 1) / ctas) * p.n_blocks);
   p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * kStageCBytes;
-  const int stage_bytes = kATileBytes + (p.block_n / ctas) * 128;
+  p.a_slot = p.halo ? (p.TH + 2) * p.TW * 128 : kATileBytes;
+  p.b_slot = (p.halo ? 3 : 1) * (p.block_n / ctas) * 128;
+  const int stage_bytes = p.a_slot + p.b_slot;
   p.stages = ring_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.act = (a->act == CFT_ACT_SILU && g_silu_tanh) ? 3 : a->act;
@@ -599,6 +657,11 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     rc = encode_map(&maps.a[0], xb, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
     if (rc) return rc;
     maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+    if (p.halo) {
+      cuuint32_t hbox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + 2), 1};
+      rc = encode_map(&maps.a[1], xb, 4, dims, str, hbox, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
+      if (rc) return rc;
+    }
   } else {
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
