@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFT_ABI_VERSION 1
+#define CFT_ABI_VERSION 2
 
 enum {
   CFT_OK = 0,
@@ -60,7 +60,9 @@ int cft_check_device(int* sm_count, int* cc_major, int* cc_minor);
  *   x   : bf16 NHWC [B,H,W,ldx], channels [x_coff, x_coff+Cin)
  *   w   : bf16 packed [Cout][k*k][Cin_p] (Cin_p = Cin rounded up to 8; tap = ky*k+kx)
  *   bias: f32 [Cout] or NULL
- *   k in {1,3}; stride in {1,2}; pad = k/2; Ho = ceil(H/stride), Wo = ceil(W/stride)
+ *   k in {1,3} = kernel height; kw = kernel width (0 -> square, kw = k; 1 with k = 3 -> a 3x1 filter, used by Focus);
+ *   stride in {1,2} (square 3x3 only); pad = (k/2, kw/2); Ho = ceil(H/stride), Wo = ceil(W/stride)
+ *   w   : tap = ky*kw + kx
  *   res : optional residual, added AFTER the activation; dtype = out_dtype
  *   y   : [B,Ho,Wo,ldy] channels [y_coff, y_coff+Cout), bf16 or f32
  * ------------------------------------------------------------------------------------- */
@@ -69,6 +71,7 @@ typedef struct cft_conv_args {
   const void* w; const float* bias; int Cout, k, stride, act;
   const void* res; int ldr, r_coff;
   void* y; int ldy, y_coff, out_dtype;
+  int kw;
 } cft_conv_args;
 
 /* tcgen05 / TMA / TMEM implicit-GEMM kernel (the product path). */
@@ -77,14 +80,18 @@ int cft_conv2d(const cft_conv_args* a, void* stream);
  * cross-check the tcgen05 kernel.  Never called by the forward path. */
 int cft_conv2d_ref(const cft_conv_args* a, void* stream);
 
-/* Focus space-to-depth gather (models/common.py:179): NCHW image [B,3,H,W] -> NHWC bf16
- * [B,H/2,W/2,16]; channel = (dy + 2*dx)*3 + c, 12..15 = 0.  in_dtype: CFT_DT_F32 / CFT_DT_BF16
- * (values already in [0,1]) or CFT_DT_U8 -- the data loader's wire format (utils/datasets.py:1272-1281),
- * scaled by 1/255 here as train.py:715 / test.py:107-108 do on the device.  batch_stride = elements
- * between consecutive images (3*H*W for a dense tensor; 6*H*W when RGB / IR are the two halves of the
- * loader's [B,6,H,W] tensor, train.py:716-717). */
+/* Focus space-to-depth gather (models/common.py:179): NCHW image [B,3,H,W] -> NHWC bf16 at half resolution.
+ * Space-to-depth channel s(dy,dx,c) = (dy + 2*dx)*3 + c (12 channels, padded to 16 with zeros).
+ *   layout 0: [B,H/2,W/2,16]  = s(.) of the pixel itself
+ *   layout 1: [B,H/2,W/2,64]  = x-direction im2col: channel kx*16 + s holds s(.) of pixel x+kx-1 (kx = 0..2, zero
+ *             outside the image), 48..63 = 0.  The Focus 3x3 conv then becomes a 3x1 conv with K = 64 whose
+ *             three vertical taps share one TMA box (128-byte TMA rows instead of 32-byte ones).
+ * in_dtype: CFT_DT_F32 / CFT_DT_BF16 (values already in [0,1]) or CFT_DT_U8 -- the data loader's wire format
+ * (utils/datasets.py:1272-1281), scaled by 1/255 here as train.py:715 / test.py:107-108 do on the device.
+ * batch_stride = elements between consecutive images (3*H*W for a dense tensor; 6*H*W when RGB / IR are the two
+ * halves of the loader's [B,6,H,W] tensor, train.py:716-717). */
 int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long long batch_stride,
-                     void* y, void* stream);
+                     int layout, void* y, void* stream);
 
 /* MaxPool k x k, stride 1, pad k/2 (-inf padding) on an NHWC bf16 channel slice
  * (SPP, models/common.py:160-165).  src/dst may be slices of the same buffer. */

@@ -30,6 +30,7 @@ class ConvArgs(C.Structure):
         ("act", C.c_int),
         ("res", C.c_void_p), ("ldr", C.c_int), ("r_coff", C.c_int),
         ("y", C.c_void_p), ("ldy", C.c_int), ("y_coff", C.c_int), ("out_dtype", C.c_int),
+        ("kw", C.c_int),
     ]
 
 
@@ -41,7 +42,7 @@ SIGNATURES = {
     "cft_check_device": ([C.POINTER(_I)] * 3, _I),
     "cft_conv2d": ([C.POINTER(ConvArgs), _P], _I),
     "cft_conv2d_ref": ([C.POINTER(ConvArgs), _P], _I),
-    "cft_focus_gather": ([_P, _I, _I, _I, _I, _LL, _P, _P], _I),
+    "cft_focus_gather": ([_P, _I, _I, _I, _I, _LL, _I, _P, _P], _I),
     "cft_maxpool_s1": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_maxpool_cascade3": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_upsample2x": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),

@@ -49,7 +49,7 @@ struct __align__(64) TensorMaps {
 
 struct ConvParams {
   int B, Ho, Wo, Cout;
-  int taps, kchunks, stride;
+  int taps, kw, kchunks, stride;   // taps = kh * kw (tap = ky * kw + kx)
   int kelems, layout;       // K elements per unit (16 / 32 / 64) and the matching UMMA swizzle code
   int ups;                  // K units (taps) per ring stage
   int halo;                 // 3x3 s1 'row-reuse' mode: a stage = one filter column kx; the three ky taps are
@@ -149,7 +149,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   // K is walked in units of (tap, kelems-wide channel chunk); a ring stage holds p.ups consecutive units
   // (several taps per stage when the channel count is small, so that per-stage barrier traffic is amortised).
   const int k_units = p.taps * p.kchunks;
-  const int k_iters = p.halo ? 3 * p.kchunks : (k_units + p.ups - 1) / p.ups;
+  const int k_iters = p.halo ? p.kw * p.kchunks : (k_units + p.ups - 1) / p.ups;
   const uint32_t row_bytes = static_cast<uint32_t>(p.kelems) * 2u;   // operand tile row: 32 / 64 / 128 B
   const uint32_t a_unit_bytes = 128u * row_bytes;                     // one unit's A tile (128 pixel rows)
   const uint32_t b_unit_bytes = static_cast<uint32_t>(b_rows) * row_bytes;
@@ -163,11 +163,11 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
       auto tap_offsets = [&](int tap, int& mi, int& dy, int& dx) {
         mi = 0; dy = 0; dx = 0;
-        if (p.taps == 9) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
+        if (p.taps > 1) {
+          const int ky = tap / p.kw, kx = tap - p.kw * ky;
           if (p.stride == 1) {
             dy = ky - 1;
-            dx = kx - 1;
+            dx = kx - (p.kw >> 1);
           } else {  // input row 2*oy + ky - 1 = 2*(oy + dy) + py
             const int py = (ky != 1), px = (kx != 1);
             dy = (ky == 0) ? -1 : 0;
@@ -179,24 +179,25 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       if (p.halo) {
         // stage = (filter column kx, 64-channel chunk): ONE (TH+2) x TW pixel box serves the three taps ky = 0..2
         const uint32_t tx_halo = static_cast<uint32_t>((p.TH + 2) * p.TW + 3 * b_rows) * 128u;
-        for (int kx = 0; kx < 3; ++kx) {
+        for (int kx = 0; kx < p.kw; ++kx) {
+          const int dxh = kx - (p.kw >> 1);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             if (elect_one_sync()) {
               uint8_t* sa = smem_a + stage * a_stage_bytes;
               uint8_t* sb = smem_b + stage * b_stage_bytes;
               if constexpr (kCtas == 2) {
-                tma_load_4d_2sm(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + kx - 1, t.y0 - 1, t.b);
+                tma_load_4d_2sm(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + dxh, t.y0 - 1, t.b);
                 for (int ky = 0; ky < 3; ++ky)
-                  tma_load_3d_2sm(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * 3 + kx,
+                  tma_load_3d_2sm(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * p.kw + kx,
                                   t.n0 + rank * b_rows);
                 if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_halo);
                 else mbar_arrive_cluster(&full_bar[stage], 0);
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], tx_halo);
-                tma_load_4d(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + kx - 1, t.y0 - 1, t.b);
+                tma_load_4d(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + dxh, t.y0 - 1, t.b);
                 for (int ky = 0; ky < 3; ++ky)
-                  tma_load_3d(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * 3 + kx, t.n0);
+                  tma_load_3d(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * p.kw + kx, t.n0);
               }
             }
             __syncwarp();
@@ -570,8 +571,10 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   CFT_REQUIRE(a && a->x && a->w && a->y, "cft_conv2d: null pointer");
   CFT_REQUIRE(a->k == 1 || a->k == 3, "cft_conv2d: k must be 1 or 3 (got %d)", a->k);
-  CFT_REQUIRE(a->stride == 1 || (a->stride == 2 && a->k == 3), "cft_conv2d: stride %d with k %d unsupported",
-              a->stride, a->k);
+  const int kw = a->kw > 0 ? a->kw : a->k;
+  CFT_REQUIRE(kw == a->k || (a->k == 3 && kw == 1), "cft_conv2d: kernel %dx%d unsupported", a->k, kw);
+  CFT_REQUIRE(a->stride == 1 || (a->stride == 2 && a->k == 3 && kw == 3), "cft_conv2d: stride %d with k %dx%d unsupported",
+              a->stride, a->k, kw);
   CFT_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "cft_conv2d: empty shape");
   CFT_REQUIRE(a->Cin % 8 == 0 && a->ldx % 8 == 0 && a->x_coff % 8 == 0,
               "cft_conv2d: Cin/ldx/x_coff must be multiples of 8 (got %d/%d/%d)", a->Cin, a->ldx, a->x_coff);
@@ -592,7 +595,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.Ho = (a->H + s - 1) / s;
   p.Wo = (a->W + s - 1) / s;
   p.Cout = a->Cout;
-  p.taps = a->k * a->k;
+  p.taps = a->k * kw;
+  p.kw = kw;
   p.kelems = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
   p.layout = p.kelems == 64 ? 2 : (p.kelems == 32 ? 4 : 6);   // UMMA LayoutType: SW128 / SW64 / SW32
   p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
@@ -620,7 +624,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.m_tiles = static_cast<int>(m_tiles);
   // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem
   // traffic per MMA -- worth it once the layer is tensor-bound (enough K work per tile) and has >= 2 tiles.
-  const int k_iters = p.halo ? 3 * p.kchunks : (p.taps * p.kchunks + p.ups - 1) / p.ups;
+  const int k_iters = p.halo ? kw * p.kchunks : (p.taps * p.kchunks + p.ups - 1) / p.ups;
   int ctas = (g_force_ctas == 1) ? 1 : 2;
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;

@@ -20,6 +20,37 @@ inline int grid_for(long long work, int threads, int max_blocks_per_sm = 16) {
 // One thread per output pixel: reads a 2x2 patch of each of the 3 planes (two float2 / bf162
 // loads per plane, consecutive threads -> consecutive addresses), writes 32 B (16 bf16).
 template <typename T>
+__device__ __forceinline__ void focus_patch(const T* __restrict__ img, long long bstride, int b, int H, int W, int oy, int ox,
+                                            float* f /*[12]*/) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const T* p0 = img + static_cast<long long>(b) * bstride + (static_cast<long long>(c) * H + 2 * oy) * W + 2 * ox;
+    const T* p1 = p0 + W;
+    float a00, a01, a10, a11;
+    if constexpr (sizeof(T) == 1) {
+      const uchar2 r0 = *reinterpret_cast<const uchar2*>(p0);
+      const uchar2 r1 = *reinterpret_cast<const uchar2*>(p1);
+      a00 = r0.x / 255.0f; a01 = r0.y / 255.0f; a10 = r1.x / 255.0f; a11 = r1.y / 255.0f;
+    } else if constexpr (sizeof(T) == 4) {
+      const float2 r0 = *reinterpret_cast<const float2*>(p0);
+      const float2 r1 = *reinterpret_cast<const float2*>(p1);
+      a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
+    } else {
+      const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p0));
+      const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p1));
+      a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
+    }
+    // channel = (dy + 2*dx)*3 + c   (models/common.py:179: [::2,::2],[1::2,::2],[::2,1::2],[1::2,1::2])
+    f[0 * 3 + c] = a00;
+    f[1 * 3 + c] = a10;
+    f[2 * 3 + c] = a01;
+    f[3 * 3 + c] = a11;
+  }
+}
+
+// One thread per output pixel.  kLayout 0: 16 channels (32 B).  kLayout 1: 64 channels (128 B) = the patches of
+// x-1, x, x+1 side by side (x-direction im2col), neighbours re-read through L1.
+template <typename T, int kLayout>
 __global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     long long bstride) {
   const int Ho = H / 2, Wo = W / 2;
@@ -30,35 +61,33 @@ __global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __
     long long t = idx / Wo;
     const int oy = static_cast<int>(t % Ho);
     const int b = static_cast<int>(t / Ho);
-    float f[16];
+    if constexpr (kLayout == 0) {
+      float f[16];
+      focus_patch(img, bstride, b, H, W, oy, ox, f);
+      f[12] = f[13] = f[14] = f[15] = 0.f;
+      bf16x8* out = reinterpret_cast<bf16x8*>(y + idx * 16);
+      out[0] = pack8(f);
+      out[1] = pack8(f + 8);
+    } else {
+      bf16x8* out = reinterpret_cast<bf16x8*>(y + idx * 64);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const T* p0 = img + static_cast<long long>(b) * bstride + (static_cast<long long>(c) * H + 2 * oy) * W + 2 * ox;
-      const T* p1 = p0 + W;
-      float a00, a01, a10, a11;
-      if constexpr (sizeof(T) == 1) {
-        const uchar2 r0 = *reinterpret_cast<const uchar2*>(p0);
-        const uchar2 r1 = *reinterpret_cast<const uchar2*>(p1);
-        a00 = r0.x / 255.0f; a01 = r0.y / 255.0f; a10 = r1.x / 255.0f; a11 = r1.y / 255.0f;
-      } else if constexpr (sizeof(T) == 4) {
-        const float2 r0 = *reinterpret_cast<const float2*>(p0);
-        const float2 r1 = *reinterpret_cast<const float2*>(p1);
-        a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
-      } else {
-        const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p0));
-        const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p1));
-        a00 = r0.x; a01 = r0.y; a10 = r1.x; a11 = r1.y;
+      for (int kx = 0; kx < 3; ++kx) {
+        float f[16];
+        const int xx = ox + kx - 1;
+        if (xx >= 0 && xx < Wo) {
+          focus_patch(img, bstride, b, H, W, oy, xx, f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) f[i] = 0.f;
+        }
+        f[12] = f[13] = f[14] = f[15] = 0.f;
+        out[2 * kx] = pack8(f);
+        out[2 * kx + 1] = pack8(f + 8);
       }
-      // channel = (dy + 2*dx)*3 + c   (models/common.py:179: [::2,::2],[1::2,::2],[::2,1::2],[1::2,1::2])
-      f[0 * 3 + c] = a00;
-      f[1 * 3 + c] = a10;
-      f[2 * 3 + c] = a01;
-      f[3 * 3 + c] = a11;
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      out[6] = pack8(z);
+      out[7] = pack8(z);
     }
-    f[12] = f[13] = f[14] = f[15] = 0.f;
-    bf16x8* out = reinterpret_cast<bf16x8*>(y + idx * 16);
-    out[0] = pack8(f);
-    out[1] = pack8(f + 8);
   }
 }
 
@@ -198,11 +227,11 @@ __global__ void addcopy_kernel(const __nv_bfloat16* __restrict__ a, int lda, con
 }
 
 // ------------------------------------------------------------------ CUDA-core conv (test cross-check only)
-__global__ void conv_ref_kernel(cft_conv_args a, int Ho, int Wo, int cin_p) {
+__global__ void conv_ref_kernel(cft_conv_args a, int Ho, int Wo, int cin_p, int kw) {
   const long long total = static_cast<long long>(a.B) * Ho * Wo * a.Cout;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
   const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(a.w);
-  const int pad = a.k / 2, taps = a.k * a.k;
+  const int pad = a.k / 2, padw = kw / 2, taps = a.k * kw;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(idx % a.Cout);
@@ -213,11 +242,11 @@ __global__ void conv_ref_kernel(cft_conv_args a, int Ho, int Wo, int cin_p) {
     const int b = static_cast<int>(t / Ho);
     float acc = 0.f;
     for (int ky = 0; ky < a.k; ++ky)
-      for (int kx = 0; kx < a.k; ++kx) {
-        const int iy = oy * a.stride + ky - pad, ix = ox * a.stride + kx - pad;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int iy = oy * a.stride + ky - pad, ix = ox * a.stride + kx - padw;
         if (iy < 0 || iy >= a.H || ix < 0 || ix >= a.W) continue;
         const __nv_bfloat16* xp = x + ((static_cast<long long>(b) * a.H + iy) * a.W + ix) * a.ldx + a.x_coff;
-        const __nv_bfloat16* wp = w + (static_cast<long long>(n) * taps + ky * a.k + kx) * cin_p;
+        const __nv_bfloat16* wp = w + (static_cast<long long>(n) * taps + ky * kw + kx) * cin_p;
         for (int c = 0; c < a.Cin; ++c) acc += __bfloat162float(xp[c]) * __bfloat162float(wp[c]);
       }
     if (a.bias) acc += a.bias[n];
@@ -236,8 +265,8 @@ __global__ void conv_ref_kernel(cft_conv_args a, int Ho, int Wo, int cin_p) {
 
 using namespace cft;
 
-extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long long batch_stride, void* y,
-                                void* stream_v) {
+extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long long batch_stride, int layout,
+                                void* y, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   CFT_REQUIRE(img && y, "cft_focus_gather: null pointer");
   CFT_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "cft_focus_gather: H, W must be even");
@@ -245,18 +274,22 @@ extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int
               "cft_focus_gather: misaligned pointer");
   CFT_REQUIRE(batch_stride >= 3LL * H * W && batch_stride % 2 == 0, "cft_focus_gather: bad batch stride");
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2);
+  CFT_REQUIRE(layout == 0 || layout == 1, "cft_focus_gather: bad layout %d", layout);
   LaunchScope ls(CFT_K_FOCUS, stream);
-  if (in_dtype == CFT_DT_F32)
-    focus_gather_kernel<float><<<grid_for(total, kThreads), kThreads, 0, stream>>>(
-        reinterpret_cast<const float*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, batch_stride);
-  else if (in_dtype == CFT_DT_BF16)
-    focus_gather_kernel<__nv_bfloat16><<<grid_for(total, kThreads), kThreads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, batch_stride);
-  else if (in_dtype == CFT_DT_U8)
-    focus_gather_kernel<uint8_t><<<grid_for(total, kThreads), kThreads, 0, stream>>>(
-        reinterpret_cast<const uint8_t*>(img), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, batch_stride);
-  else
-    return fail_arg("cft_focus_gather: bad in_dtype %d", in_dtype);
+  const int grid = grid_for(total, kThreads);
+  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+#define CFT_FOCUS_LAUNCH(T)                                                                                        \
+  do {                                                                                                             \
+    if (layout == 0)                                                                                               \
+      focus_gather_kernel<T, 0><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(img), yo, B, H, W, batch_stride); \
+    else                                                                                                           \
+      focus_gather_kernel<T, 1><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(img), yo, B, H, W, batch_stride); \
+  } while (0)
+  if (in_dtype == CFT_DT_F32) CFT_FOCUS_LAUNCH(float);
+  else if (in_dtype == CFT_DT_BF16) CFT_FOCUS_LAUNCH(__nv_bfloat16);
+  else if (in_dtype == CFT_DT_U8) CFT_FOCUS_LAUNCH(uint8_t);
+  else return fail_arg("cft_focus_gather: bad in_dtype %d", in_dtype);
+#undef CFT_FOCUS_LAUNCH
   return ls.finish("cft_focus_gather launch");
 }
 
@@ -366,6 +399,7 @@ extern "C" int cft_conv2d_ref(const cft_conv_args* a, void* stream_v) {
   const int cin_p = (a->Cin + 7) / 8 * 8;
   const long long total = static_cast<long long>(a->B) * Ho * Wo * a->Cout;
   LaunchScope ls(CFT_K_CONV_REF, stream);
-  conv_ref_kernel<<<grid_for(total, kThreads, 32), kThreads, 0, stream>>>(*a, Ho, Wo, cin_p);
+  const int kw = a->kw > 0 ? a->kw : a->k;
+  conv_ref_kernel<<<grid_for(total, kThreads, 32), kThreads, 0, stream>>>(*a, Ho, Wo, cin_p, kw);
   return ls.finish("cft_conv2d_ref launch");
 }

@@ -92,7 +92,9 @@ class Conv(nn.Module):
 
 
 class Focus(nn.Module):
-    """reference models/common.py:168-180: space-to-depth gather kernel + 3x3 conv on 16 (12 used) channels."""
+    """reference models/common.py:168-180.  The 2x2 space-to-depth gather is one kernel that also lays the patches
+    of x-1, x, x+1 side by side (64 channels, 48 used), so the 3x3 conv over 12 channels becomes a 3x1 conv over
+    K = 64 whose three vertical taps share one TMA box (the 16-channel layout needs 9 boxes of 32-byte rows)."""
 
     def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
         super().__init__()
@@ -103,16 +105,26 @@ class Focus(nn.Module):
         if x.shape[1] != 3:
             raise CftError("Focus: the two-stream path feeds 3-channel images (models/yolo_test.py:499-500)")
         ops._require_cuda(x, "Focus input")
-        g = ops.focus_gather(x)
         cv = self.conv
         k, s, act = cv._check()
         bn = getattr(cv, "bn", None)
         srcs = [cv.conv.weight, cv.conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+        wide = (k == 3 and s == 1)
 
         def build():
             bnp = (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None else None
-            return ops.pack_conv_weight(cv.conv.weight, cv.conv.bias, bnp, cin_pad_to=16, device=x.device)
-        w, b = self._packed.get((_versions(*srcs), str(x.device)), build)
+            w, b = ops.pack_conv_weight(cv.conv.weight, cv.conv.bias, bnp, cin_pad_to=16, device=x.device)
+            if wide:                       # [Cout][ky*3+kx][16] -> [Cout][ky][kx*16 + c] (+16 zero columns)
+                co = w.shape[0]
+                w3 = torch.zeros(co, 3, 64, dtype=w.dtype, device=w.device)
+                w3[:, :, :48] = w.view(co, 3, 3, 16).reshape(co, 3, 48)
+                w = w3.contiguous()
+            return w, b
+        w, b = self._packed.get((_versions(*srcs), str(x.device), wide), build)
+        if wide:
+            g = ops.focus_gather(x, layout=1)
+            return ops.conv2d(g, w, b, 3, 1, act, out=out, cout=cv.conv.out_channels, cin=64, kw=1)
+        g = ops.focus_gather(x, layout=0)
         return ops.conv2d(g, w, b, k, s, act, out=out, cout=cv.conv.out_channels, cin=16)
 
 

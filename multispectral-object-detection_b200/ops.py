@@ -98,8 +98,9 @@ def pack_linear_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device=Non
 # ------------------------------------------------------------------------------ conv / gemm
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, act: int,
            out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, cout: Optional[int] = None,
-           cin: Optional[int] = None, impl: str = "tcgen05") -> torch.Tensor:
-    """y = act(conv(x, w) + bias) [+ residual] on NHWC bf16; ``out`` may be a channel-slice view."""
+           cin: Optional[int] = None, impl: str = "tcgen05", kw: int = 0) -> torch.Tensor:
+    """y = act(conv(x, w) + bias) [+ residual] on NHWC bf16; ``out`` may be a channel-slice view.
+    ``k`` is the kernel height, ``kw`` its width (0 = square)."""
     lib = _lib.lib()
     xp, ldx = nhwc_desc(x)
     b, c, h, wd = x.shape
@@ -121,6 +122,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: in
     else:
         a.res, a.ldr, a.r_coff = None, 0, 0
     a.y, a.ldy, a.y_coff, a.out_dtype = yp, ldy, 0, DT_BF16
+    a.kw = kw
     fn = lib.cft_conv2d if impl == "tcgen05" else lib.cft_conv2d_ref
     _lib.check(fn(C.byref(a), _stream()), "cft_conv2d")
     return out
@@ -153,15 +155,17 @@ def gemm(a_mat: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act
         args.res, args.ldr, args.r_coff = None, 0, 0
     args.y, args.ldy, args.y_coff = out.data_ptr(), out.stride(0), 0
     args.out_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
+    args.kw = 0
     fn = lib.cft_conv2d if impl == "tcgen05" else lib.cft_conv2d_ref
     _lib.check(fn(C.byref(args), _stream()), "cft_conv2d(gemm)")
     return out
 
 
 # ------------------------------------------------------------------------------ movers
-def focus_gather(img: torch.Tensor) -> torch.Tensor:
-    """NCHW image [B,3,H,W] -> NHWC bf16 [B,16,H/2,W/2] (12 used).  fp32 / bf16 values in [0,1], or uint8
-    (the loader's wire format, scaled by 1/255 in the kernel).  The batch stride may be larger than 3*H*W
+def focus_gather(img: torch.Tensor, layout: int = 0) -> torch.Tensor:
+    """NCHW image [B,3,H,W] -> NHWC bf16 at half resolution: layout 0 = [B,16,H/2,W/2] (12 used), layout 1 =
+    [B,64,H/2,W/2] x-direction im2col (patches of x-1, x, x+1 side by side; 48 used).  fp32 / bf16 values in [0,1],
+    or uint8 (the loader's wire format, scaled by 1/255 in the kernel).  The batch stride may be larger than 3*H*W
     (the RGB / IR halves of the loader's [B,6,H,W] tensor) -- no copy is made for such views."""
     lib = _lib.lib()
     _require_cuda(img, "image")
@@ -174,8 +178,8 @@ def focus_gather(img: torch.Tensor) -> torch.Tensor:
         img = img.contiguous()
     bstride = img.stride(0) if b > 1 else 3 * h * w
     dt = {torch.float32: DT_F32, torch.bfloat16: DT_BF16, torch.uint8: _lib.DT_U8}[img.dtype]
-    y = empty_nhwc(b, 16, h // 2, w // 2, img.device)
-    _lib.check(lib.cft_focus_gather(img.data_ptr(), dt, b, h, w, bstride, y.data_ptr(), _stream()),
+    y = empty_nhwc(b, 64 if layout == 1 else 16, h // 2, w // 2, img.device)
+    _lib.check(lib.cft_focus_gather(img.data_ptr(), dt, b, h, w, bstride, layout, y.data_ptr(), _stream()),
                "cft_focus_gather")
     return y
 

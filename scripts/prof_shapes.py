@@ -26,6 +26,7 @@ SHAPES = [
     ("c3_p4_cv12_512_512", 512, 512, 40, 40, 1, 1),
     ("spp_cv2_2048_1024", 2048, 1024, 20, 20, 1, 1),
     ("focus_16_64", 16, 64, 320, 320, 3, 1),
+    ("focus_wide_64_64_3x1", 64, 64, 320, 320, 31, 1),
     ("gpt_p5_up_1024_4096", 1024, 4096, 1, 4096, 1, 1),
     ("gpt_p5_down_4096_1024", 4096, 1024, 1, 4096, 1, 1),
     ("gpt_p3_qkv_256_768", 256, 768, 1, 4096, 1, 1),
@@ -41,10 +42,14 @@ def main():
         if only and name not in only:
             continue
         b = 1 if h == 1 else B
+        kw = 0
+        if k == 31:
+            k, kw = 3, 1
+        kww = kw if kw else k
         x = torch.randn(b, cin, h, w, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        wt = torch.randn(cout, cin, k, k) / math.sqrt(cin * k * k)
+        wt = torch.randn(cout, cin, k, kww) / math.sqrt(cin * k * kww)
         wp, bp = ops.pack_conv_weight(wt, torch.zeros(cout), None, device=DEV)
-        y = ops.conv2d(x, wp, bp, k, s, act, cout=cout)            # warm-up
+        y = ops.conv2d(x, wp, bp, k, s, act, cout=cout, kw=kw)            # warm-up
         torch.cuda.synchronize()
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,18 +58,18 @@ def main():
             for _ in range(5):
                 flush.zero_()                                     # L2 flush between timed iterations
                 e0.record()
-                ops.conv2d(x, wp, bp, k, s, act, out=y, cout=cout)
+                ops.conv2d(x, wp, bp, k, s, act, out=y, cout=cout, kw=kw)
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = sorted(ts)[len(ts) // 2]
             ho, wo = (h + s - 1) // s, (w + s - 1) // s
-            flops = 2.0 * b * ho * wo * cout * cin * k * k
-            byts = 2.0 * (b * h * w * cin + b * ho * wo * cout + cout * cin * k * k)
+            flops = 2.0 * b * ho * wo * cout * cin * k * kww
+            byts = 2.0 * (b * h * w * cin + b * ho * wo * cout + cout * cin * k * kww)
             print(f"{name:28s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s ({flops/ms/1e9*1e12/peaks_t*100:5.1f}% tensor)  "
                   f"{byts/ms/1e6:8.1f} GB/s ({byts/ms/1e6*1e9/peaks_b*100:5.1f}% hbm)  AI {flops/byts:6.0f}", flush=True)
         else:
-            ops.conv2d(x, wp, bp, k, s, act, out=y, cout=cout)
+            ops.conv2d(x, wp, bp, k, s, act, out=y, cout=cout, kw=kw)
             torch.cuda.synchronize()
 
 

@@ -29,14 +29,15 @@ def timed(fn, key_fn):
     return wrap
 
 
-def conv_key(x, w, bias, k, stride, act, out=None, residual=None, cout=None, cin=None, impl="tcgen05"):
+def conv_key(x, w, bias, k, stride, act, out=None, residual=None, cout=None, cin=None, impl="tcgen05", kw=0):
     b, c, h, wd = x.shape
     cin = cin or c
     cout = cout or w.shape[0]
     ho, wo = (h + stride - 1) // stride, (wd + stride - 1) // stride
-    fl = 2.0 * b * ho * wo * cout * cin * k * k
-    by = 2.0 * (b * h * wd * cin + b * ho * wo * cout * (2 if residual is not None else 1) + cout * cin * k * k)
-    return (f"conv {cin:4d}->{cout:4d} k{k}s{stride} {h}x{wd}" + (" +res" if residual is not None else ""), fl, by)
+    kww = kw if kw else k
+    fl = 2.0 * b * ho * wo * cout * cin * k * kww
+    by = 2.0 * (b * h * wd * cin + b * ho * wo * cout * (2 if residual is not None else 1) + cout * cin * k * kww)
+    return (f"conv {cin:4d}->{cout:4d} k{k}x{kww}s{stride} {h}x{wd}" + (" +res" if residual is not None else ""), fl, by)
 
 
 def gemm_key(a, w, bias, act=0, out=None, residual=None, out_dtype=torch.bfloat16, n=None, impl="tcgen05"):

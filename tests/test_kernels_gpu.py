@@ -127,12 +127,58 @@ def test_gemm_linear(M, K, N, act, f32out, cft):
 def test_focus_gather(dtype, cft):
     img = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(1)).to(DEV).to(dtype)
     y = cft.ops.focus_gather(img)
+    y64 = cft.ops.focus_gather(img, layout=1)
     torch.cuda.synchronize()
     x = img.float()
     ref = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)   # common.py:179
+    ref = ref.to(torch.bfloat16).float()
     assert y.shape == (2, 16, 16, 24)
-    assert torch.equal(y[:, :12].float(), ref.to(torch.bfloat16).float())
+    assert torch.equal(y[:, :12].float(), ref)
     assert (y[:, 12:] == 0).all()
+    # layout 1: channel kx*16 + s = space-to-depth channel s of pixel x + kx - 1 (zero outside the image)
+    assert y64.shape == (2, 64, 16, 24)
+    padded = F.pad(ref, (1, 1))
+    for kx in range(3):
+        assert torch.equal(y64[:, kx * 16:kx * 16 + 12].float(), padded[..., kx:kx + 24]), kx
+        assert (y64[:, kx * 16 + 12:kx * 16 + 16] == 0).all()
+    assert (y64[:, 48:] == 0).all()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 64, 64, 32, 48), (1, 64, 32, 20, 24), (2, 128, 128, 16, 16)])
+def test_conv_3x1_filter(B, Cin, Cout, H, W, cft):
+    """k = 3, kw = 1 (the Focus conv after the x-direction im2col): with and without the row-reuse tile shape."""
+    ops = cft.ops
+    x = nhwc(rnd(B, Cin, H, W, seed=1))
+    w = rnd(Cout, Cin, 3, 1, seed=2, scale=1.0 / math.sqrt(Cin * 3))
+    b = rnd(Cout, seed=3, scale=0.5)
+    wp, bp = ops.pack_conv_weight(w, b, None, device=DEV)
+    assert wp.shape == (Cout, 3, Cin)
+    y = ops.conv2d(x, wp, bp, 3, 1, 1, cout=Cout, kw=1)
+    y_ref_kernel = ops.conv2d(x, wp, bp, 3, 1, 1, cout=Cout, kw=1, impl="ref")
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(x.float(), wp.float().reshape(Cout, 3, 1, Cin).permute(0, 3, 1, 2), bp, padding=(1, 0)))
+    close_bf16(y_ref_kernel, ref, "cuda-core ref 3x1")
+    close_bf16(y, ref, "tcgen05 3x1")
+
+
+def test_focus_module_matches_torch(cft):
+    """Focus = gather (x-im2col layout) + 3x1 tcgen05 conv == SiLU(BN(conv3x3(space_to_depth(x)))) (common.py:168-180)."""
+    torch.manual_seed(0)
+    m = cft.Focus(3, 64, 3).eval()
+    m.conv.bn.eps = 1e-3
+    with torch.no_grad():
+        m.conv.bn.running_mean.normal_(0, .1); m.conv.bn.running_var.uniform_(.5, 1.5)
+        m.conv.bn.weight.uniform_(.5, 1.5); m.conv.bn.bias.normal_(0, .1)
+    m = m.to(DEV)
+    img = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(1)).to(DEV)
+    with torch.no_grad():
+        y = m(img)
+        x = img.to(torch.bfloat16).float()
+        s2d = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
+        ref = F.silu(F.batch_norm(F.conv2d(s2d, m.conv.conv.weight.to(torch.bfloat16).float(), None, padding=1),
+                                  m.conv.bn.running_mean, m.conv.bn.running_var, m.conv.bn.weight, m.conv.bn.bias, False, 0., 1e-3))
+    torch.cuda.synchronize()
+    close_bf16(y, ref, "Focus module")
 
 
 def test_maxpool_cascade_equals_5_9_13(cft):
