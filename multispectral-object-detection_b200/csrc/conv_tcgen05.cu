@@ -145,6 +145,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous kernel
+  // in the stream; from here on this kernel reads / overwrites activations, so wait for its predecessors to finish.
+  pdl_launch_dependents();
+  pdl_wait();
 
   // K is walked in units of (tap, kelems-wide channel chunk); a ring stage holds p.ups consecutive units
   // (several taps per stage when the channel count is small, so that per-stage barrier traffic is amortised).
@@ -561,6 +565,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
+const bool g_no_pdl = getenv("CFT_NO_PDL") != nullptr;
 const bool g_no_halo = getenv("CFT_NO_ROW_REUSE") != nullptr;
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
@@ -721,27 +726,33 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   int units = sm_count() / ctas;           // persistent: one CTA (or CTA pair) per SM (pair)
   if (units > p.num_tiles) units = p.num_tiles;
   LaunchScope ls(CFT_K_CONV_TCGEN05, stream);
-  if (ctas == 1) {
-    cft_conv_tcgen05_kernel<1><<<units, kThreads, smem_bytes, stream>>>(maps, p);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(units * 2);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, cft_conv_tcgen05_kernel<2>, maps, p);
-    if (e != cudaSuccess) {
-      ls.finish("cft_conv2d launch");
-      return check_cuda(e, "cudaLaunchKernelEx(conv_tcgen05<2>)");
-    }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(units * ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (ctas == 2) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2;
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+  }
+  if (!g_no_pdl) {   // programmatic dependent launch: this kernel's prologue overlaps the previous kernel's tail
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  cudaError_t e = (ctas == 2) ? cudaLaunchKernelEx(&cfg, cft_conv_tcgen05_kernel<2>, maps, p)
+                              : cudaLaunchKernelEx(&cfg, cft_conv_tcgen05_kernel<1>, maps, p);
+  if (e != cudaSuccess) {
+    ls.finish("cft_conv2d launch");
+    return check_cuda(e, "cudaLaunchKernelEx(conv_tcgen05)");
   }
   return ls.finish("cft_conv2d launch");
 }

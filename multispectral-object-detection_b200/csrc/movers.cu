@@ -48,45 +48,37 @@ __device__ __forceinline__ void focus_patch(const T* __restrict__ img, long long
   }
 }
 
-// One thread per output pixel.  kLayout 0: 16 channels (32 B).  kLayout 1: 64 channels (128 B) = the patches of
-// x-1, x, x+1 side by side (x-direction im2col), neighbours re-read through L1.
+// kLayout 0: one thread per output pixel, 16 channels (32 B).
+// kLayout 1: four threads per output pixel, each writes 32 B of the 128-byte pixel: slots 0..2 = the patch of
+// x-1, x, x+1 (x-direction im2col), slot 3 = zeros.  A warp writes 8 pixels = 1 KiB contiguous.
 template <typename T, int kLayout>
 __global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     long long bstride) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = static_cast<long long>(B) * Ho * Wo;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long npix = static_cast<long long>(B) * Ho * Wo;
+  const long long total = kLayout == 0 ? npix : npix * 4;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < total;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long idx = kLayout == 0 ? it : (it >> 2);
+    const int slot = kLayout == 0 ? 0 : static_cast<int>(it & 3);
     const int ox = static_cast<int>(idx % Wo);
     long long t = idx / Wo;
     const int oy = static_cast<int>(t % Ho);
     const int b = static_cast<int>(t / Ho);
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = 0.f;
     if constexpr (kLayout == 0) {
-      float f[16];
       focus_patch(img, bstride, b, H, W, oy, ox, f);
-      f[12] = f[13] = f[14] = f[15] = 0.f;
       bf16x8* out = reinterpret_cast<bf16x8*>(y + idx * 16);
       out[0] = pack8(f);
       out[1] = pack8(f + 8);
     } else {
-      bf16x8* out = reinterpret_cast<bf16x8*>(y + idx * 64);
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        float f[16];
-        const int xx = ox + kx - 1;
-        if (xx >= 0 && xx < Wo) {
-          focus_patch(img, bstride, b, H, W, oy, xx, f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 12; ++i) f[i] = 0.f;
-        }
-        f[12] = f[13] = f[14] = f[15] = 0.f;
-        out[2 * kx] = pack8(f);
-        out[2 * kx + 1] = pack8(f + 8);
-      }
-      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      out[6] = pack8(z);
-      out[7] = pack8(z);
+      const int xx = ox + slot - 1;
+      if (slot < 3 && xx >= 0 && xx < Wo) focus_patch(img, bstride, b, H, W, oy, xx, f);
+      bf16x8* out = reinterpret_cast<bf16x8*>(y + idx * 64 + slot * 16);
+      out[0] = pack8(f);
+      out[1] = pack8(f + 8);
     }
   }
 }
@@ -276,7 +268,7 @@ extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2);
   CFT_REQUIRE(layout == 0 || layout == 1, "cft_focus_gather: bad layout %d", layout);
   LaunchScope ls(CFT_K_FOCUS, stream);
-  const int grid = grid_for(total, kThreads);
+  const int grid = grid_for(layout == 0 ? total : total * 4, kThreads);
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
 #define CFT_FOCUS_LAUNCH(T)                                                                                        \
   do {                                                                                                             \

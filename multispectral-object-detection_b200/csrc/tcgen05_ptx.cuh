@@ -169,6 +169,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (and run its prologue) before the preceding kernel in the stream has finished; it must not touch that kernel's
+// results before pdl_wait().  pdl_launch_dependents() lets the NEXT kernel begin launching early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ CTA-pair (cta_group::2) variants
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's CTA 0
 
