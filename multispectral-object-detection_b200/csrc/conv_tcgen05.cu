@@ -153,7 +153,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   // K is walked in units of (tap, kelems-wide channel chunk); a ring stage holds p.ups consecutive units
   // (several taps per stage when the channel count is small, so that per-stage barrier traffic is amortised).
   const int k_units = p.taps * p.kchunks;
-  const int k_iters = p.halo ? p.kw * p.kchunks : (k_units + p.ups - 1) / p.ups;
+  const int k_iters = p.halo ? (p.kw * p.kchunks + p.ups - 1) / p.ups : (k_units + p.ups - 1) / p.ups;
   const uint32_t row_bytes = static_cast<uint32_t>(p.kelems) * 2u;   // operand tile row: 32 / 64 / 128 B
   const uint32_t a_unit_bytes = 128u * row_bytes;                     // one unit's A tile (128 pixel rows)
   const uint32_t b_unit_bytes = static_cast<uint32_t>(b_rows) * row_bytes;
@@ -181,34 +181,43 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         }
       };
       if (p.halo) {
-        // stage = (filter column kx, 64-channel chunk): ONE (TH+2) x TW pixel box serves the three taps ky = 0..2
-        const uint32_t tx_halo = static_cast<uint32_t>((p.TH + 2) * p.TW + 3 * b_rows) * 128u;
-        for (int kx = 0; kx < p.kw; ++kx) {
-          const int dxh = kx - (p.kw >> 1);
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            if (elect_one_sync()) {
-              uint8_t* sa = smem_a + stage * a_stage_bytes;
-              uint8_t* sb = smem_b + stage * b_stage_bytes;
+        // a unit = (filter column kx, channel chunk): ONE (TH+2) x TW pixel box serves the three taps ky = 0..2;
+        // small-Cin layers (kchunks == 1) put up to p.ups filter columns into one ring stage
+        const uint32_t a_box = static_cast<uint32_t>((p.TH + 2) * p.TW) * row_bytes;
+        const uint32_t tx_halo = a_box + 3u * b_unit_bytes;                       // per CTA, per unit
+        const int n_hunits = p.kw * p.kchunks;
+        for (int u0 = 0; u0 < n_hunits; u0 += p.ups) {
+          const int n_units = (n_hunits - u0) < p.ups ? (n_hunits - u0) : p.ups;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (elect_one_sync()) {
+            if constexpr (kCtas == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_halo * n_units);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], tx_halo * n_units);
+            }
+            for (int j = 0; j < n_units; ++j) {
+              const int u = u0 + j;
+              const int kx = u / p.kchunks, kc = u - kx * p.kchunks;
+              const int dxh = kx - (p.kw >> 1);
+              uint8_t* sa = smem_a + stage * a_stage_bytes + j * a_box;
+              uint8_t* sb = smem_b + stage * b_stage_bytes + j * 3 * b_unit_bytes;
               if constexpr (kCtas == 2) {
-                tma_load_4d_2sm(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + dxh, t.y0 - 1, t.b);
+                tma_load_4d_2sm(sa, &maps.a[1], &full_bar[stage], kc * p.kelems, t.x0 + dxh, t.y0 - 1, t.b);
                 for (int ky = 0; ky < 3; ++ky)
-                  tma_load_3d_2sm(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * p.kw + kx,
+                  tma_load_3d_2sm(sb + ky * b_unit_bytes, &maps.b, &full_bar[stage], kc * p.kelems, ky * p.kw + kx,
                                   t.n0 + rank * b_rows);
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_halo);
-                else mbar_arrive_cluster(&full_bar[stage], 0);
               } else {
-                mbar_arrive_expect_tx(&full_bar[stage], tx_halo);
-                tma_load_4d(sa, &maps.a[1], &full_bar[stage], kc * 64, t.x0 + dxh, t.y0 - 1, t.b);
+                tma_load_4d(sa, &maps.a[1], &full_bar[stage], kc * p.kelems, t.x0 + dxh, t.y0 - 1, t.b);
                 for (int ky = 0; ky < 3; ++ky)
-                  tma_load_3d(sb + ky * b_rows * 128, &maps.b, &full_bar[stage], kc * 64, ky * p.kw + kx, t.n0);
+                  tma_load_3d(sb + ky * b_unit_bytes, &maps.b, &full_bar[stage], kc * p.kelems, ky * p.kw + kx, t.n0);
               }
             }
-            __syncwarp();
-            if (++stage == stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       } else if (p.ups == 1) {
@@ -293,17 +302,24 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          if (p.halo) {             // 3 taps (ky) x 4 K-steps out of one pixel box: tap ky starts TW(=8) rows = 1024 B further
-            const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
-            const uint32_t b_tap = static_cast<uint32_t>(b_rows) * 128u >> 4;
+          if (p.halo) {             // per unit: 3 taps (ky) out of one pixel box; tap ky starts TW(=8) rows further
+            const int n_hunits = p.kw * p.kchunks;
+            const int u0 = it * p.ups;
+            const int n_units = (n_hunits - u0) < p.ups ? (n_hunits - u0) : p.ups;
+            const uint32_t a_box16 = (static_cast<uint32_t>((p.TH + 2) * p.TW) * row_bytes) >> 4;
+            const uint32_t b_tap16 = b_unit_bytes >> 4;
+            const uint32_t ky_step16 = (8u * row_bytes) >> 4;     // one 8-row swizzle group per tile row
+            for (int j = 0; j < n_units; ++j) {
+              const uint32_t a_lo = a_lo0 + stage * a_lo_stride + j * a_box16;
+              const uint32_t b_lo = b_lo0 + stage * b_lo_stride + j * 3 * b_tap16;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + ky * 64 + 2 * k);
-                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + ky * b_tap + 2 * k);
-                if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | ky | k) != 0 ? 1u : 0u);
-                else umma_bf16(d_tmem, da, db, idesc, (it | ky | k) != 0 ? 1u : 0u);
+              for (int ky = 0; ky < 3; ++ky) {
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + ky * ky_step16 + 2 * k);
+                  const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + ky * b_tap16 + 2 * k);
+                  if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | j | ky | k) != 0 ? 1u : 0u);
+                  else umma_bf16(d_tmem, da, db, idesc, (it | j | ky | k) != 0 ? 1u : 0u);
+                }
               }
             }
           } else if (p.kelems == 64) {     // one (tap, 64-channel) unit per stage: 4 back-to-back MMAs, no inner loops
@@ -609,7 +625,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.stride = s;
   // row-reuse mode for L2-bound 3x3 stride-1 layers (measured L2->SM ceiling ~60 B/cycle/SM): 8 x 16 pixel tiles,
   // the 3 vertical taps share one (16+2) x 8 pixel box -> 2.7x less activation traffic than 9 separate boxes
-  p.halo = (!g_no_halo && a->k == 3 && s == 1 && p.kelems == 64 && p.Wo % 8 == 0 && p.Ho % 16 == 0) ? 1 : 0;
+  p.halo = (!g_no_halo && a->k == 3 && s == 1 && p.Wo % 8 == 0 && p.Ho % 16 == 0) ? 1 : 0;
   if (p.halo) {
     p.TW = 8;
     p.TH = 16;
@@ -629,15 +645,15 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.m_tiles = static_cast<int>(m_tiles);
   // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem
   // traffic per MMA -- worth it once the layer is tensor-bound (enough K work per tile) and has >= 2 tiles.
-  const int k_iters = p.halo ? kw * p.kchunks : (p.taps * p.kchunks + p.ups - 1) / p.ups;
+  const int k_iters = p.halo ? (kw * p.kchunks + p.ups - 1) / p.ups : (p.taps * p.kchunks + p.ups - 1) / p.ups;
   int ctas = (g_force_ctas == 1) ? 1 : 2;
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
   p.num_tiles = static_cast<int>(((m_tiles + ctas - 1) / ctas) * p.n_blocks);
   p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * kStageCBytes;
-  p.a_slot = p.halo ? (p.TH + 2) * p.TW * 128 : kATileBytes;
-  p.b_slot = (p.halo ? 3 : 1) * (p.block_n / ctas) * 128;
+  p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;
+  p.b_slot = p.halo ? ((p.ups * 3 * (p.block_n / ctas) * p.kelems * 2 + 1023) / 1024) * 1024 : (p.block_n / ctas) * 128;
   const int stage_bytes = p.a_slot + p.b_slot;
   p.stages = ring_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -667,7 +683,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     if (rc) return rc;
     maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
     if (p.halo) {
-      cuuint32_t hbox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + 2), 1};
+      cuuint32_t hbox[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + 2), 1};
       rc = encode_map(&maps.a[1], xb, 4, dims, str, hbox, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
       if (rc) return rc;
     }

@@ -92,9 +92,10 @@ class Conv(nn.Module):
 
 
 class Focus(nn.Module):
-    """reference models/common.py:168-180.  The 2x2 space-to-depth gather is one kernel that also lays the patches
-    of x-1, x, x+1 side by side (64 channels, 48 used), so the 3x3 conv over 12 channels becomes a 3x1 conv over
-    K = 64 whose three vertical taps share one TMA box (the 16-channel layout needs 9 boxes of 32-byte rows)."""
+    """reference models/common.py:168-180: space-to-depth gather kernel (16 channels, 12 used; reads the loader's
+    uint8 wire format directly) + 3x3 tcgen05 conv in row-reuse mode (three 18x8-pixel boxes per tile).
+    ``wide = True`` selects the alternative x-direction-im2col layout (64 channels) + 3x1 conv."""
+    wide = False
 
     def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
         super().__init__()
@@ -109,7 +110,7 @@ class Focus(nn.Module):
         k, s, act = cv._check()
         bn = getattr(cv, "bn", None)
         srcs = [cv.conv.weight, cv.conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
-        wide = (k == 3 and s == 1)
+        wide = bool(self.wide) and k == 3 and s == 1
 
         def build():
             bnp = (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None else None

@@ -161,10 +161,12 @@ def test_conv_3x1_filter(B, Cin, Cout, H, W, cft):
     close_bf16(y, ref, "tcgen05 3x1")
 
 
-def test_focus_module_matches_torch(cft):
-    """Focus = gather (x-im2col layout) + 3x1 tcgen05 conv == SiLU(BN(conv3x3(space_to_depth(x)))) (common.py:168-180)."""
+@pytest.mark.parametrize("wide", [False, True])
+def test_focus_module_matches_torch(wide, cft):
+    """Focus = gather + tcgen05 conv == SiLU(BN(conv3x3(space_to_depth(x)))) (common.py:168-180), both layouts."""
     torch.manual_seed(0)
     m = cft.Focus(3, 64, 3).eval()
+    m.wide = wide
     m.conv.bn.eps = 1e-3
     with torch.no_grad():
         m.conv.bn.running_mean.normal_(0, .1); m.conv.bn.running_var.uniform_(.5, 1.5)
