@@ -196,3 +196,31 @@ def test_forward_engine_graph_pipeline(cft, oracle):
             assert torch.equal(z, z_ref.cpu())
             assert torch.equal(z_ref, z_f)
     assert torch.equal(eng.infer(batches[0]), outs[0])
+
+
+def test_llvip_1024x1280_properties(cft, oracle):
+    """BASELINE config 3 geometry (yolov5l-x3 LLVIP cfg, nc=1, 1024x1280): 80640 output rows,
+    batch invariance, finiteness; P3 pooling bins are uniform 16x20 here."""
+    cfg, sd, model = build(cft, oracle, "yolov5l_fusion_transformerx3_llvip", 51)
+    x, x2 = (t.to(DEV) for t in oracle.make_inputs(2, 1024, 1280, seed=52))
+    with torch.no_grad():
+        z, raw = model(x, x2)
+        z1, _ = model(x[1:2].contiguous(), x2[1:2].contiguous())
+    torch.cuda.synchronize()
+    assert z.shape == (2, 80640, 6)
+    assert [tuple(r.shape) for r in raw] == [(2, 3, 128, 160, 6), (2, 3, 64, 80, 6), (2, 3, 32, 40, 6)]
+    assert bool(torch.isfinite(z).all())
+    assert torch.equal(z[1:2], z1)
+
+
+def test_yolov5x_640_batch_sweep_properties(cft, oracle):
+    """BASELINE config 5 graph (derived yolov5x x3: widths 80..1280, head dims 40/80/160 -> SIMT attention fallback,
+    K tails): the batch-1 result equals row 0 of the batch-3 result bit-exactly."""
+    cfg, sd, model = build(cft, oracle, "yolov5x_fusion_transformerx3_FLIR_aligned", 61)
+    x, x2 = (t.to(DEV) for t in oracle.make_inputs(3, 640, 640, seed=62))
+    with torch.no_grad():
+        z3, _ = model(x, x2)
+        z1, _ = model(x[0:1].contiguous(), x2[0:1].contiguous())
+    torch.cuda.synchronize()
+    assert z3.shape == (3, 25200, 8) and bool(torch.isfinite(z3).all())
+    assert torch.equal(z3[0:1], z1)
