@@ -5,7 +5,7 @@
 
 * the whole 47-layer forward (~350 kernel launches) is captured once per buffer slot into a CUDA graph
   (launch-bound at small batch, SURVEY.md §3A) and replayed;
-* two device input/output slots + a copy stream: the host->device copy of batch i+1 and the
+* two device input/output slots + two copy streams (H2D, D2H): the host->device copy of batch i+1 and the
   device->host copy of detections i-1 overlap the compute of batch i;
 * ``infer(host_u8)`` is the blocking call a user makes; ``submit()/collect()`` expose the pipeline.
 
@@ -30,7 +30,8 @@ class ForwardEngine:
         self.slots = slots
         self.use_graph = use_graph
         self.compute = torch.cuda.Stream(self.device)
-        self.copy = torch.cuda.Stream(self.device)
+        self.h2d = torch.cuda.Stream(self.device)     # separate copy streams: a D2H queued behind a compute event
+        self.d2h = torch.cuda.Stream(self.device)     # must not block the next batch's H2D
         self.x_dev = [torch.zeros(self.shape, dtype=torch.uint8, device=self.device) for _ in range(slots)]
         self.z_dev: List[Optional[torch.Tensor]] = [None] * slots
         self.graphs: List[Optional[torch.cuda.CUDAGraph]] = [None] * slots
@@ -91,10 +92,10 @@ class ForwardEngine:
         self._next = (self._next + 1) % self.slots
         if s in self._pending:
             raise CftError("submit: all slots in flight; collect() first")
-        with torch.cuda.stream(self.copy):
-            self.copy.wait_event(self.ev_free[s])           # slot's previous result has left the device
+        with torch.cuda.stream(self.h2d):
+            self.h2d.wait_event(self.ev_free[s])            # slot's previous result has left the device
             self.x_dev[s].copy_(host_u8, non_blocking=True)
-            self.ev_in[s].record(self.copy)
+            self.ev_in[s].record(self.h2d)
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(self.ev_in[s])
             if self.use_graph:
@@ -103,10 +104,10 @@ class ForwardEngine:
                 with torch.no_grad():
                     self.z_dev[s] = self._forward(s)
             self.ev_done[s].record(self.compute)
-        with torch.cuda.stream(self.copy):
-            self.copy.wait_event(self.ev_done[s])
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.ev_done[s])
             self.z_host[s].copy_(self.z_dev[s], non_blocking=True)
-            self.ev_free[s].record(self.copy)
+            self.ev_free[s].record(self.d2h)
         self._pending.append(s)
         return s
 
@@ -126,4 +127,5 @@ class ForwardEngine:
         while self._pending:
             self.collect()
         self.compute.synchronize()
-        self.copy.synchronize()
+        self.h2d.synchronize()
+        self.d2h.synchronize()
