@@ -170,6 +170,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="after the measurements, run ONE eager step between cudaProfilerStart/Stop (for ncu "
+                         "--profile-from-start off launch lists; numbers printed under ncu are never bench values)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -297,13 +300,25 @@ def main():
         conv_ms, conv_n = prof["conv_tcgen05"]
         conv_flops_step = (flops_pair - attn_core) * B
         achieved = conv_flops_step * nprof / (conv_ms / 1e3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
+        if os.path.isfile(tpath):          # summed dram__bytes_{read,write} of the kernel's launches in one step (ncu)
+            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
         roofline = {"kernel": "cft_conv_tcgen05_kernel", "bound": "tensor", "achieved": achieved,
                     "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                    "peak_source": peaks["source"] + " sustained bf16", "traffic": None,
+                    "peak_source": peaks["source"] + " sustained bf16", "traffic": traffic,
+                    "traffic_note": "sum over the kernel's launches of one step (profiles/r01_conv_dram_traffic.json)",
                     "launches_per_step": conv_n // nprof, "ms_per_step_in_kernel": conv_ms / nprof,
                     "algorithmic_gflop_per_step": conv_flops_step / 1e9,
                     "whole_forward_tensor_frac": (flops_pair * value / world) / (peaks["tflops_sustained"] * 1e12)}
 
+    if args.ncu_range and rank == 0:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        with torch.no_grad():
+            step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     if world > 1:
         dist.barrier()
     if rank == 0:
