@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 from copy import deepcopy
 from pathlib import Path
 from typing import Dict, List, Optional
@@ -141,35 +142,76 @@ class Model(nn.Module):
                            "(models/yolo_test.py:222 drops x2); not on the hot path")
         return self.forward_once(x, x2, profile)
 
+    # run the IR branch between fusion points on a side CUDA stream (fills the tail waves); CFT_ONE_STREAM=1 disables
+    two_streams = os.environ.get("CFT_ONE_STREAM") is None
+
     def forward_once(self, x, x2, profile=False):
-        """Layer walk of reference models/yolo_test.py:235-272 with buffer planning on top."""
+        """Layer walk of reference models/yolo_test.py:235-272 with buffer planning on top.
+
+        The RGB and IR chains between two CFT blocks are independent; the IR chain is issued on a side stream
+        (fork after its source layer, join at the GPT) so that its persistent kernels fill the SMs left idle by
+        the tail wave of the RGB chain's kernels (and vice versa).  Fork/join uses CUDA events only, so the walk is
+        capturable into a CUDA graph."""
         plan = self._plan
         y: List = []
         concat_bufs: Dict[int, torch.Tensor] = {}
         fused: Dict[int, torch.Tensor] = {}
+        chains = plan["ir_chains"] if (self.two_streams and x.is_cuda) else {}
+        main = torch.cuda.current_stream() if chains else None
+        side = self._side_stream(x.device) if chains else None
+        src_events: Dict[int, torch.cuda.Event] = {}
+        wanted_src = {src for (_, src) in chains.values()}
+        chain_end, side_active = -1, False
+        if chains and -4 in wanted_src:
+            src_events[-4] = main.record_event()
         for m in self.model:
             i = m.i
             if m.f != -1 and m.f != -4:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             if m.f == -4:
                 x = x2
-            if i in fused:                                     # Add2 / Add already produced by the fused GPT pass
-                x = fused.pop(i)
-            elif i in plan["gpt_groups"]:
-                g = plan["gpt_groups"][i]
-                outs = {}
-                for key in ("rgb", "ir", "sum"):
-                    outs[key] = self._slot(plan, concat_bufs, g[key], x[0]) if g[key] in plan["slots"] else None
-                o_rgb, o_ir, o_sum = m.forward_fused(x[0], x[1], out_rgb=outs["rgb"], out_ir=outs["ir"], out_sum=outs["sum"])
-                fused[g["rgb"]], fused[g["ir"]], fused[g["sum"]] = o_rgb, o_ir, o_sum
-                x = None                                       # the raw GPT tuple is never materialised
-            elif i in plan["slots"]:
-                ref = x[0] if isinstance(x, (list, tuple)) else x
-                x = m(x, out=self._slot(plan, concat_bufs, i, ref, m))
-            else:
-                x = m(x)
+            if i in chains:                                    # fork: the IR chain starts here
+                chain_end, src = chains[i]
+                side.wait_event(src_events[src])
+                side_active = True
+            if side_active and isinstance(m, M.GPT):           # join at the fusion block
+                main.wait_stream(side)
+                side_active = False
+            on_side = side_active and i <= chain_end
+            ctx = torch.cuda.stream(side) if on_side else _NullCtx()
+            with ctx:
+                if i in fused:                                 # Add2 / Add already produced by the fused GPT pass
+                    x = fused.pop(i)
+                elif i in plan["gpt_groups"]:
+                    g = plan["gpt_groups"][i]
+                    outs = {}
+                    for key in ("rgb", "ir", "sum"):
+                        outs[key] = self._slot(plan, concat_bufs, g[key], x[0]) if g[key] in plan["slots"] else None
+                    o_rgb, o_ir, o_sum = m.forward_fused(x[0], x[1], out_rgb=outs["rgb"], out_ir=outs["ir"], out_sum=outs["sum"])
+                    fused[g["rgb"]], fused[g["ir"]], fused[g["sum"]] = o_rgb, o_ir, o_sum
+                    if chains:
+                        for key in ("rgb", "ir"):              # these feed the next RGB / IR chains
+                            if g[key] in wanted_src:
+                                src_events[g[key]] = main.record_event()
+                    x = None                                   # the raw GPT tuple is never materialised
+                elif i in plan["slots"]:
+                    ref = x[0] if isinstance(x, (list, tuple)) else x
+                    x = m(x, out=self._slot(plan, concat_bufs, i, ref, m))
+                else:
+                    x = m(x)
+            if chains and not on_side and i in wanted_src and i not in src_events:
+                src_events[i] = main.record_event()
             y.append(x if i in self.save else None)
+        if side_active:                                        # graph without a closing GPT (not the x3 layout)
+            main.wait_stream(side)
         return x
+
+    def _side_stream(self, device):
+        st = getattr(self, "_side", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device)
+            object.__setattr__(self, "_side", st)
+        return st
 
     def _slot(self, plan, bufs, i, ref, m=None):
         """Channel-slice view of the Concat buffer that layer i's output is planned into."""
@@ -209,6 +251,14 @@ class Model(nn.Module):
         n_p = sum(x.numel() for x in self.parameters())
         logger.info(f"Model Summary: {len(list(self.modules()))} layers, {n_p} parameters")
         return n_p
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 def fuse_conv_and_bn(conv, bn):
@@ -300,7 +350,24 @@ def _plan_graph(layers: nn.Sequential) -> dict:
             if ok:
                 slots[s] = (m.i, c0, c0 + out_ch[s], ctot, 1)
             c0 += out_ch[s]
-    return {"slots": slots, "gpt_groups": gpt_groups, "out_ch": out_ch}
+    # Two-stream execution: the IR branch between two fusion points is a chain of single-input layers that does not
+    # depend on the RGB chain listed just before it in the yaml (rows 5-9, 15-16, 23-25).  chains[first] = (last, src):
+    # layers first..last may run on a side CUDA stream once layer ``src`` (or the IR image, src = -4) is available;
+    # the GPT that consumes ``last`` joins the streams.
+    chains = {}
+    for m in layers:
+        if not isinstance(m, M.GPT):
+            continue
+        ia = m.f[1]
+        first = ia
+        while isinstance(layers[first].f, int) and layers[first].f == -1 and first > 0:
+            first -= 1
+        src = layers[first].f
+        if not isinstance(src, int) or first <= m.f[0]:
+            continue                                       # not the "RGB chain, then IR chain" layout
+        if all(isinstance(layers[i], (M.Conv, M.C3, M.SPP, M.Focus)) for i in range(first, ia + 1)):
+            chains[first] = (ia, src)
+    return {"slots": slots, "gpt_groups": gpt_groups, "out_ch": out_ch, "ir_chains": chains}
 
 
 # ------------------------------------------------------------------------------------ drop-in
