@@ -28,17 +28,20 @@ using namespace cft::ptx;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = one 128B swizzle row
-constexpr int kEpiGroups = 4;          // column groups of 4 warps (one warp per TMEM lane quarter) each
+constexpr int kEpiGroups = 4;          // epilogue groups of 4 warps (one warp per TMEM lane quarter) each:
+                                       // 2 teams (alternate tiles) x 2 column groups
+constexpr int kEpiTeams = 2;
+constexpr int kEpiColGroups = kEpiGroups / kEpiTeams;
 constexpr int kEpilogueWarps = 4 * kEpiGroups;
 constexpr int kThreads = 128 + 32 * kEpilogueWarps;   // TMA, MMA, TMEM-alloc, idle + epilogue warps
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kAccCols = 256;          // TMEM columns per accumulator buffer
+constexpr int kMaxAccStages = 4;       // TMEM accumulator ring: 2 x 256 columns, or 4 x 128 when block_n <= 128
 constexpr int kTmemCols = 512;
 constexpr int kSmemTotal = 227 * 1024;    // dynamic smem per CTA on sm_100
 constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
 
-constexpr int kTailBytes = 256 + 1024;     // barriers + TMEM slot, bias staging
+constexpr int kTailBytes = 256 + 2048;     // barriers + TMEM slot, bias staging (one copy per epilogue team)
 
 struct __align__(64) TensorMaps {
   CUtensorMap a[4];
@@ -52,6 +55,7 @@ struct ConvParams {
   int taps, kw, kchunks, stride;   // taps = kh * kw (tap = ky * kw + kx)
   int kelems, layout;       // K elements per unit (16 / 32 / 64) and the matching UMMA swizzle code
   int ups;                  // K units (taps) per ring stage
+  int acc_stages, acc_cols; // TMEM accumulator ring (acc_stages * acc_cols = 512 columns)
   int halo;                 // 3x3 s1 'row-reuse' mode: a stage = one filter column kx; the three ky taps are
                             // 8-row-group offsets into one (TH+2) x TW pixel box (TW = 8)
   int a_slot, b_slot;       // ring slot sizes in bytes
@@ -114,11 +118,11 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiGroups * kStageCBytes);
   uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2] MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2] epilogue -> MMA
-  uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [kEpiGroups] residual TMA -> epilogue group
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kEpiGroups);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6 + kEpiGroups);   // [256] bias of the current n-block
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;                        // [kMaxAccStages] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxAccStages;       // [kMaxAccStages] epilogue -> MMA
+  uint64_t* res_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages;      // [kEpiGroups] residual TMA -> epilogue group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 2);   // [256] bias
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -129,9 +133,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       mbar_init(&full_bar[i], kCtas);      // pair: both producers arrive on CTA 0's barrier
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpilogueWarps * kCtas);   // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tempty_bar[i], (kEpilogueWarps / kEpiTeams) * kCtas);   // one arrive per warp of the consuming team
     }
     for (int i = 0; i < kEpiGroups; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
@@ -297,7 +301,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccCols);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -359,23 +363,26 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           phase ^= 1u;
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: kEpiGroups column groups x 4 warps =====================
     const int ew = warp - 4;
-    const int grp = ew >> 2;               // column group: handles 32-column chunks grp, grp + kEpiGroups, ...
+    const int grp = ew >> 2;               // epilogue group 0..3
+    const int team = grp & 1;              // team t drains the accumulators of this CTA's tiles t, t+2, t+4, ...
+    const int cg = grp >> 1;               // column group inside the team: 32-column chunks cg, cg + 2, ...
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;         // accumulator row = pixel within the tile
     const int gtid = (ew & 3) * 32 + lane; // thread index within the group
     uint8_t* stage_c = smem_c + grp * kStageCBytes;   // this group's staging buffer
     uint64_t* rbar = &res_bar[grp];
+    float* bias_t = bias_s + team * 256;   // the team's bias copy (teams may be on different n-blocks)
     uint32_t res_phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
     const int chunks_total = (p.block_n + 31) >> 5;                  // 32-column chunks
-    const int my_chunks = chunks_total > grp ? (chunks_total - grp + kEpiGroups - 1) / kEpiGroups : 0;
+    const int my_chunks = chunks_total > cg ? (chunks_total - cg + kEpiColGroups - 1) / kEpiColGroups : 0;
     const int cps = p.out_f32 ? 1 : 2;                               // chunks per staging buffer (16 KiB)
     const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
     const uint32_t c_chunk_stride = 128u * c_row_bytes;
@@ -383,11 +390,16 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const bool use_res = p.res != nullptr;
     int bias_n0 = -1;
     const int bar_id = 1 + grp;
-    for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
+    const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages == 4 ? 2 : 1;
+    for (int j = team;; j += kEpiTeams) {          // j = index in this CTA's tile sequence (the MMA warp walks all j)
+      const int tile = work0 + j * work_stride;
+      if (tile >= p.num_tiles) break;
+      const int acc = j & acc_mask;
+      const uint32_t acc_phase = static_cast<uint32_t>(j >> acc_shift) & 1u;
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kAccCols);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.acc_cols);
       bool waited_full = false;
-      for (int sg = 0; sg < my_chunks; sg += cps) {        // this group's chunks: grp + kEpiGroups * (sg + i)
+      for (int sg = 0; sg < my_chunks; sg += cps) {        // this group's chunks: cg + kEpiColGroups * (sg + i)
         const int nch = (my_chunks - sg) < cps ? (my_chunks - sg) : cps;
         // acquire the group's staging buffer (its previous store has been read out); prefetch the residual tile
         if (gtid == 0) {
@@ -395,15 +407,15 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           if (use_res) {
             mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
             for (int i = 0; i < nch; ++i)
-              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (grp + kEpiGroups * (sg + i)) * 32, t.x0,
+              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (cg + kEpiColGroups * (sg + i)) * 32, t.x0,
                           t.y0, t.b);
           }
         }
         if (t.n0 != bias_n0) {          // (re)stage this n-block's bias; published by the barrier below
           for (int i = gtid; i < my_chunks * 32; i += 128) {
-            const int col = (grp + kEpiGroups * (i >> 5)) * 32 + (i & 31);
+            const int col = (cg + kEpiColGroups * (i >> 5)) * 32 + (i & 31);
             const int n = t.n0 + col;
-            bias_s[col] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+            bias_t[col] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
           }
           bias_n0 = t.n0;
         }
@@ -418,14 +430,14 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           res_phase ^= 1u;
         }
         for (int ci = 0; ci < nch; ++ci) {
-          const int c0 = (grp + kEpiGroups * (sg + ci)) * 32;
+          const int c0 = (cg + kEpiColGroups * (sg + ci)) * 32;
           uint8_t* stage = stage_c + ci * c_chunk_stride;
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
           // bias (staged in smem once per n-block; zero beyond Cout) + activation on all 32 columns: straight-line,
           // 32 independent dependency chains (columns past Cout/block_n hold garbage that the TMA store clips).
           float f[32];
-          const float4* bs = reinterpret_cast<const float4*>(bias_s + c0);
+          const float4* bs = reinterpret_cast<const float4*>(bias_t + c0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b4 = bs[i];
@@ -477,7 +489,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         named_bar_sync(bar_id, 128);
         if (gtid == 0 && !p.dbg_skip_store) {
           for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
-            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (grp + kEpiGroups * (sg + i)) * 32, t.x0, t.y0, t.b);
+            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (cg + kEpiColGroups * (sg + i)) * 32, t.x0, t.y0, t.b);
           bulk_commit();
         }
       }
@@ -491,8 +503,6 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the MMA issuer lives in CTA 0
         else mbar_arrive(&tempty_bar[acc]);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
     if (gtid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
   }
@@ -581,6 +591,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
+const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
 const bool g_no_pdl = getenv("CFT_NO_PDL") != nullptr;
 const bool g_no_halo = getenv("CFT_NO_ROW_REUSE") != nullptr;
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
@@ -641,6 +652,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
          p.block_n >= 128 && (p.block_n / 2) % 32 == 0 && a->Cout % (p.block_n / 2) == 0)
     p.block_n /= 2;
   p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
+  p.acc_stages = (p.block_n <= 128 && !g_acc2) ? 4 : 2;
+  p.acc_cols = 512 / p.acc_stages;
   CFT_REQUIRE(m_tiles * p.n_blocks < (1LL << 31), "cft_conv2d: too many tiles");
   p.m_tiles = static_cast<int>(m_tiles);
   // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for s in c3_p3_1x1_128 c3_p3_3x3_128 focus_16_64; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:cft_conv_tcgen05 -s 1 -c 1 -f -o gpurun_out/prof_$s python scripts/prof_shapes.py $s > gpurun_out/ncu_$s.log 2>&1
+for s in c3_p3_1x1_128 c3_p4_3x3_256; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:cft_conv_tcgen05 -s 1 -c 1 -f -o gpurun_out/prof3_$s python scripts/prof_shapes.py $s > gpurun_out/ncu3_$s.log 2>&1
   echo "$s exit $?"
 done
-ls -la gpurun_out/*.ncu-rep
+bash scripts/gpu_ncu_step.sh
