@@ -288,6 +288,10 @@ def main():
         peaks = load_peaks()
         flops_pair = O.conv_linear_flops(cfg, H, W)
         attn_core = sum(8 * 4.0 * 128 * 128 * d for d in (256, 512, 1024))
+        # per-launch CUDA events only add up when launches are serialised: the profiled pass walks the graph on ONE
+        # stream (the timed region overlaps the RGB and IR branches on two)
+        two = model.two_streams
+        model.two_streams = False
         pkg._lib.prof_enable(True)
         nprof = 3
         with torch.no_grad():
@@ -296,6 +300,7 @@ def main():
         torch.cuda.synchronize()
         prof = pkg._lib.prof_get()
         pkg._lib.prof_enable(False)
+        model.two_streams = two
         kernel_ms = {k: round(v[0] / nprof, 4) for k, v in prof.items() if v[1]}
         conv_ms, conv_n = prof["conv_tcgen05"]
         conv_flops_step = (flops_pair - attn_core) * B

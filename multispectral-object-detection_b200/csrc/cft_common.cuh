@@ -51,6 +51,11 @@ __device__ __forceinline__ float silu_tanh(float v) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+__device__ __forceinline__ float silu_tanh_h(float h) {   // h = v / 2 already formed
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == CFT_ACT_SILU) return silu_f(v);

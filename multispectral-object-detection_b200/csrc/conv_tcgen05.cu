@@ -62,6 +62,7 @@ struct ConvParams {
   int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
+  uint32_t mg_nb, mg_tx, mg_ty;   // ceil(2^32 / d) for n_blocks, tiles_x, tiles_y (0 = divide)
   int m_tiles;              // spatial tiles = B * tiles_y * tiles_x; num_tiles counts (pairs of) m-tiles x n-blocks
   int act, out_f32;
   int ldy, y_coff, ldr, r_coff;
@@ -75,11 +76,19 @@ struct TileCoord {
 };
 // work item -> tile of this CTA.  With CTA pairs a work item is two consecutive spatial tiles (rank 0 / 1) of
 // one n-block; a pair's missing second tile (odd count) gets b = B: all-OOB loads (zero fill), clipped stores.
+// n / d for the tile decode: multiply-high by ceil(2^32 / d) (exact while n * d < 2^32, checked on the host, which
+// otherwise passes magic = 0 -> true division).  Four hardware divisions per tile per warp were ~100 of the
+// epilogue's ~490 instructions per warp-tile.
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+  if (d == 1) return n;
+  return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic)) : n / d;
+}
 template <int kCtas>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, int rank) {
   TileCoord t;
-  const int nb = work % p.n_blocks;
-  int m = (work / p.n_blocks) * kCtas + rank;
+  const int wq = fast_div(work, p.n_blocks, p.mg_nb);
+  const int nb = work - wq * p.n_blocks;
+  int m = wq * kCtas + rank;
   t.n0 = nb * p.block_n;
   if (m >= p.m_tiles) {
     t.b = p.B;
@@ -87,10 +96,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, 
     t.x0 = 0;
     return t;
   }
-  const int tx = m % p.tiles_x;
-  m /= p.tiles_x;
-  const int ty = m % p.tiles_y;
-  t.b = m / p.tiles_y;
+  const int mq = fast_div(m, p.tiles_x, p.mg_tx);
+  const int tx = m - mq * p.tiles_x;
+  t.b = fast_div(mq, p.tiles_y, p.mg_ty);
+  const int ty = mq - t.b * p.tiles_y;
   t.y0 = ty * p.TH;
   t.x0 = tx * p.TW;
   return t;
@@ -101,7 +110,9 @@ template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KiB alignment by offsetting the __shared__ array (a uintptr_t round trip would make the compiler lose the
+  // shared address space and emit generic LD/ST for the epilogue's staging and bias accesses)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -415,7 +426,8 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           for (int i = gtid; i < my_chunks * 32; i += 128) {
             const int col = (cg + kEpiColGroups * (i >> 5)) * 32 + (i & 31);
             const int n = t.n0 + col;
-            bias_t[col] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+            const float bv = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+            bias_t[col] = p.act == 3 ? 0.5f * bv : bv;     // tanh-SiLU consumes h = (acc + bias) / 2 = fma(acc, .5, bias / 2)
           }
           bias_n0 = t.n0;
         }
@@ -438,23 +450,31 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           // 32 independent dependency chains (columns past Cout/block_n hold garbage that the TMA store clips).
           float f[32];
           const float4* bs = reinterpret_cast<const float4*>(bias_t + c0);
+          if (p.act == 3) {     // SiLU as h + h*tanh(h), h = (acc + bias) / 2: FFMA, MUFU.TANH, FFMA per element
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = bs[i];
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-          }
-          if (p.act == CFT_ACT_SILU) {
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = bs[i];
+              f[4 * i + 0] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 0]), 0.5f, b4.x));
+              f[4 * i + 1] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, b4.y));
+              f[4 * i + 2] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, b4.z));
+              f[4 * i + 3] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, b4.w));
+            }
+          } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = silu_fast(f[i]);
-          } else if (p.act == CFT_ACT_GELU) {
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = bs[i];
+              f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+              f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+              f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+              f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+            }
+            if (p.act == CFT_ACT_SILU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
-          } else if (p.act == 3) {     // SiLU as h + h*tanh(h) (one SFU op per element)
+              for (int i = 0; i < 32; ++i) f[i] = silu_fast(f[i]);
+            } else if (p.act == CFT_ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = silu_tanh(f[i]);
+              for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+            }
           }
           // staging tile = TMA box (32 channels x TW x TH), hardware-swizzled rows:
           //   bf16: 64 B rows, SWIZZLE_64B  (16 B chunk ^= (row >> 1) & 3)
@@ -663,6 +683,16 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   if (p.kelems != 64 || p.block_n % 32 != 0 || m_tiles < 2) ctas = 1;
   if (g_force_ctas == 0 && k_iters < 4) ctas = 1;
   p.num_tiles = static_cast<int>(((m_tiles + ctas - 1) / ctas) * p.n_blocks);
+  {
+    const unsigned long long n_max = static_cast<unsigned long long>(m_tiles + 1) * p.n_blocks + 2;
+    auto magic = [&](int d) -> uint32_t {
+      if (d <= 1 || n_max * static_cast<unsigned long long>(d) >= (1ULL << 32)) return 0u;
+      return static_cast<uint32_t>(((1ULL << 32) + d - 1) / d);
+    };
+    p.mg_nb = magic(p.n_blocks);
+    p.mg_tx = magic(p.tiles_x);
+    p.mg_ty = magic(p.tiles_y);
+  }
   p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * kStageCBytes;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;
