@@ -158,6 +158,9 @@ int cft_detect_decode(const float* head, int ldh, int B, int ny, int nx, int na,
 int cft_prof_enable(int on);            /* resets counters when turned on           */
 int cft_prof_get(int kernel_id, double* total_ms, long long* launches);
 long long cft_launch_count(void);       /* kernels launched by this library so far  */
+/* debug: per-CTA clock samples (64 u64 slots per CTA, device buffer zeroed by the caller) written by the following
+ * cft_conv2d launches; NULL turns the trace off.  Used by scripts/trace_conv.py only.                            */
+int cft_debug_conv_trace(void* buf);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ struct ConvParams {
   int halo;                 // 3x3 s1 'row-reuse' mode: a stage = one filter column kx; the three ky taps are
                             // 8-row-group offsets into one (TH+2) x TW pixel box (TW = 8)
   int a_slot, b_slot;       // ring slot sizes in bytes
+  unsigned long long* trace;   // debug timeline (cft_debug_conv_trace): kTraceSlots clock samples per CTA, else null
   int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
@@ -105,6 +106,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, 
   return t;
 }
 
+constexpr int kTraceSlots = 64;
+// slot map: 0 globaltimer at entry | 1 clock at entry | 2 setup done | 3 predecessors done (PDL) | 4 first operand
+// stage landed | 5 last MMA committed | 6 epilogue drained | 7 exit | 8+2j / 9+2j accumulator j ready / released
+__device__ __forceinline__ void trace_mark(const ConvParams& p, int slot) {
+  if (p.trace != nullptr && slot < kTraceSlots) p.trace[blockIdx.x * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
+}
+
 // ------------------------------------------------------------------ the kernel
 template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -136,6 +144,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 2);   // [256] bias
 
   if (threadIdx.x == 0) {
+    if (p.trace != nullptr) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      p.trace[blockIdx.x * kTraceSlots] = gt;
+      trace_mark(p, 1);
+    }
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
     prefetch_tmap(&maps.c);
@@ -162,8 +176,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous kernel
   // in the stream; from here on this kernel reads / overwrites activations, so wait for its predecessors to finish.
+  if (threadIdx.x == 0) trace_mark(p, 2);
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(p, 3);
 
   // K is walked in units of (tap, kelems-wide channel chunk); a ring stage holds p.ups consecutive units
   // (several taps per stage when the channel count is small, so that per-stage barrier traffic is amortised).
@@ -317,7 +333,22 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          if (p.halo) {             // per unit: 3 taps (ky) out of one pixel box; tap ky starts TW(=8) rows further
+          if (tile == work0 && it == 0) trace_mark(p, 4);
+          if (p.halo && p.kelems == 64) {   // one (kx, 64-channel) unit per stage: 12 back-to-back MMAs, no inner loops
+            // (3 taps ky out of one pixel box: tap ky starts one 8-row swizzle group = 1 KiB further into it)
+            const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
+            const uint32_t b_tap16 = b_unit_bytes >> 4;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + ky * 64 + 2 * k);
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + ky * b_tap16 + 2 * k);
+                if constexpr (kCtas == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (it | ky | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem, da, db, idesc, (it | ky | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else if (p.halo) {      // per unit: 3 taps (ky) out of one pixel box; tap ky starts TW(=8) rows further
             const int n_hunits = p.kw * p.kchunks;
             const int u0 = it * p.ups;
             const int n_units = (n_hunits - u0) < p.ups ? (n_hunits - u0) : p.ups;
@@ -367,6 +398,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
             umma_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
             if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
           }
+          if (it == k_iters - 1) trace_mark(p, 5);
         }
         __syncwarp();
         if (++stage == stages) {
@@ -436,6 +468,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
           waited_full = true;
+          if (gtid == 0 && cg == 0) trace_mark(p, 8 + 2 * j);
         }
         if (use_res) {
           mbar_wait(rbar, res_phase);
@@ -523,8 +556,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the MMA issuer lives in CTA 0
         else mbar_arrive(&tempty_bar[acc]);
       }
+      if (gtid == 0 && cg == 0) trace_mark(p, 9 + 2 * j);
     }
     if (gtid == 0) bulk_wait_all();   // all bulk stores complete before the CTA exits
+    if (gtid == 0 && grp == 0) trace_mark(p, 6);
   }
 
   tc_fence_before();
@@ -534,6 +569,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   } else {
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  }
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    trace_mark(p, 7);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[blockIdx.x * kTraceSlots + kTraceSlots - 1] = gt;     // calibrates clock64 against wall time
   }
 }
 
@@ -612,6 +653,7 @@ bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
 const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
+unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace
 const bool g_no_pdl = getenv("CFT_NO_PDL") != nullptr;
 const bool g_no_halo = getenv("CFT_NO_ROW_REUSE") != nullptr;
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
@@ -641,6 +683,17 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   CFT_REQUIRE(a->stride == 1 || (a->H % 2 == 0 && a->W % 2 == 0), "cft_conv2d: stride 2 needs even H, W");
   CFT_REQUIRE(a->out_dtype == CFT_DT_BF16 || a->out_dtype == CFT_DT_F32, "cft_conv2d: bad out_dtype");
 
+  // A 1x1 stride-1 conv has no halo: walk its pixels as one flat [B*H*W, C] matrix, so that tiles are 128
+  // consecutive pixels (40x40 and 20x20 maps otherwise leave 11 % / 22 % of every 128-row MMA tile empty).
+  cft_conv_args flat;
+  if (a->k == 1 && kw == 1 && a->stride == 1 && (a->B > 1 || a->H > 1) &&
+      static_cast<long long>(a->B) * a->H * a->W < (1LL << 31)) {
+    flat = *a;
+    flat.W = a->B * a->H * a->W;
+    flat.H = 1;
+    flat.B = 1;
+    a = &flat;
+  }
   const int s = a->stride;
   ConvParams p;
   p.B = a->B;
@@ -694,6 +747,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     p.mg_ty = magic(p.tiles_y);
   }
   p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
+  p.trace = g_trace_buf;
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * kStageCBytes;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;
   p.b_slot = p.halo ? ((p.ups * 3 * (p.block_n / ctas) * p.kelems * 2 + 1023) / 1024) * 1024 : (p.block_n / ctas) * 128;
@@ -814,4 +868,11 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     return check_cuda(e, "cudaLaunchKernelEx(conv_tcgen05)");
   }
   return ls.finish("cft_conv2d launch");
+}
+
+// Debug timeline: `buf` (device, >= grid * 64 u64, zeroed by the caller) receives per-CTA clock samples of every
+// cft_conv2d launch that follows (see trace_mark for the slot map); nullptr turns it off.  Not for production use.
+extern "C" int cft_debug_conv_trace(void* buf) {
+  g_trace_buf = static_cast<unsigned long long*>(buf);
+  return CFT_OK;
 }
