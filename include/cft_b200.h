@@ -161,6 +161,8 @@ long long cft_launch_count(void);       /* kernels launched by this library so f
 /* debug: per-CTA clock samples (64 u64 slots per CTA, device buffer zeroed by the caller) written by the following
  * cft_conv2d launches; NULL turns the trace off.  Used by scripts/trace_conv.py only.                            */
 int cft_debug_conv_trace(void* buf);
+/* debug: {first CTA start, last CTA end} in %globaltimer ns of each of the next max_launches conv launches */
+int cft_debug_conv_spans(void* buf, int max_launches);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,11 @@ struct ConvParams {
   int halo;                 // 3x3 s1 'row-reuse' mode: a stage = one filter column kx; the three ky taps are
                             // 8-row-group offsets into one (TH+2) x TW pixel box (TW = 8)
   int a_slot, b_slot;       // ring slot sizes in bytes
+  int b_res_bytes;          // exact bytes of the resident weights (b_res is that, rounded up to 1 KiB)
+  int b_res;                // row-reuse mode with the WHOLE weight matrix resident in smem (loaded once per CTA;
+                            // the ring then streams activations only): b_res = its size in bytes, 0 = off
+  int stage_c;              // bytes per epilogue staging buffer (8 KiB: one bf16 32-column chunk, 16 KiB: two / one f32)
+  unsigned long long* span;    // debug (cft_debug_conv_spans): {min CTA start, max CTA end} of this launch in %globaltimer ns
   unsigned long long* trace;   // debug timeline (cft_debug_conv_trace): kTraceSlots clock samples per CTA, else null
   int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   int TW, TH, tiles_x, tiles_y;
@@ -133,17 +138,23 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.b_slot);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * a_stage_bytes;
-  uint8_t* smem_c = smem_b + stages * b_stage_bytes;  // b_stage_bytes is a multiple of 2048 -> 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiGroups * kStageCBytes);
+  uint8_t* smem_c = smem_b + (p.b_res ? p.b_res : stages * b_stage_bytes);  // both multiples of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiGroups * p.stage_c);
   uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kMaxStages;                        // [kMaxAccStages] MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kMaxStages + kMaxAccStages;       // [kMaxAccStages] epilogue -> MMA
   uint64_t* res_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages;      // [kEpiGroups] residual TMA -> epilogue group
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 2);   // [256] bias
+  uint64_t* bres_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups;   // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 1);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 4);   // [2][256] bias, 16 B aligned
 
   if (threadIdx.x == 0) {
+    if (p.span != nullptr) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      atomicMin(p.span, gt);
+    }
     if (p.trace != nullptr) {
       unsigned long long gt;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -163,6 +174,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       mbar_init(&tempty_bar[i], (kEpilogueWarps / kEpiTeams) * kCtas);   // one arrive per warp of the consuming team
     }
     for (int i = 0; i < kEpiGroups; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -178,6 +190,16 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   // in the stream; from here on this kernel reads / overwrites activations, so wait for its predecessors to finish.
   if (threadIdx.x == 0) trace_mark(p, 2);
   pdl_launch_dependents();
+  if (p.b_res && warp == 0 && elect_one_sync()) {
+    // weights are parameters, never written by a predecessor kernel: fetch them before the dependency wait
+    const uint32_t b_unit = static_cast<uint32_t>(p.block_n) * static_cast<uint32_t>(p.kelems) * 2u;
+    mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.b_res_bytes));
+    for (int u = 0; u < p.kw * p.kchunks; ++u) {
+      const int kx = u / p.kchunks, kc = u - kx * p.kchunks;
+      for (int ky = 0; ky < 3; ++ky)
+        tma_load_3d(smem_b + (u * 3 + ky) * b_unit, &maps.b, bres_bar, kc * p.kelems, ky * p.kw + kx, 0);
+    }
+  }
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(p, 3);
 
@@ -193,6 +215,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+    long long p_wait = 0, pc0 = 0;      // debug trace: cycles the producer waited for free ring slots (row-reuse path)
     const uint32_t tx_unit = static_cast<uint32_t>(p.TW * p.TH + b_rows) * row_bytes;   // per CTA, per unit
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
@@ -215,11 +238,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         // a unit = (filter column kx, channel chunk): ONE (TH+2) x TW pixel box serves the three taps ky = 0..2;
         // small-Cin layers (kchunks == 1) put up to p.ups filter columns into one ring stage
         const uint32_t a_box = static_cast<uint32_t>((p.TH + 2) * p.TW) * row_bytes;
-        const uint32_t tx_halo = a_box + 3u * b_unit_bytes;                       // per CTA, per unit
+        const uint32_t tx_halo = a_box + (p.b_res ? 0u : 3u * b_unit_bytes);      // per CTA, per unit
         const int n_hunits = p.kw * p.kchunks;
         for (int u0 = 0; u0 < n_hunits; u0 += p.ups) {
           const int n_units = (n_hunits - u0) < p.ups ? (n_hunits - u0) : p.ups;
+          if (p.trace) pc0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (p.trace) p_wait += clock64() - pc0;
           if (elect_one_sync()) {
             if constexpr (kCtas == 2) {
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_halo * n_units);
@@ -240,8 +265,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
                                   t.n0 + rank * b_rows);
               } else {
                 tma_load_4d(sa, &maps.a[1], &full_bar[stage], kc * p.kelems, t.x0 + dxh, t.y0 - 1, t.b);
-                for (int ky = 0; ky < 3; ++ky)
-                  tma_load_3d(sb + ky * b_unit_bytes, &maps.b, &full_bar[stage], kc * p.kelems, ky * p.kw + kx, t.n0);
+                if (!p.b_res)
+                  for (int ky = 0; ky < 3; ++ky)
+                    tma_load_3d(sb + ky * b_unit_bytes, &maps.b, &full_bar[stage], kc * p.kelems, ky * p.kw + kx, t.n0);
               }
             }
           }
@@ -313,6 +339,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         }
       }
     }
+    if (p.trace && lane == 0) p.trace[blockIdx.x * kTraceSlots + kTraceSlots - 4] = static_cast<unsigned long long>(p_wait);
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (CTA 0 of a pair issues for both) =====================
     int stage = 0;
@@ -325,19 +352,29 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
     const uint32_t a_lo_stride = a_stage_bytes >> 4, b_lo_stride = b_stage_bytes >> 4;
     const int ksteps = p.kelems / 16;
+    if (p.b_res) {
+      mbar_wait(bres_bar, 0);
+      tc_fence_after();
+    }
+    long long w_full = 0, w_empty = 0, c0 = 0;     // debug trace: cycles this warp waited for operands / accumulators
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
+      if (p.trace) c0 = clock64();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      if (p.trace) w_empty += clock64() - c0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_cols);
       for (int it = 0; it < k_iters; ++it) {
+        if (p.trace) c0 = clock64();
         mbar_wait(&full_bar[stage], phase);
+        if (p.trace) w_full += clock64() - c0;
         tc_fence_after();
         if (elect_one_sync()) {
           if (tile == work0 && it == 0) trace_mark(p, 4);
           if (p.halo && p.kelems == 64) {   // one (kx, 64-channel) unit per stage: 12 back-to-back MMAs, no inner loops
             // (3 taps ky out of one pixel box: tap ky starts one 8-row swizzle group = 1 KiB further into it)
-            const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
             const uint32_t b_tap16 = b_unit_bytes >> 4;
+            const uint32_t a_lo = a_lo0 + stage * a_lo_stride;
+            const uint32_t b_lo = p.b_res ? b_lo0 + it * 3 * b_tap16 : b_lo0 + stage * b_lo_stride;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -357,7 +394,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
             const uint32_t ky_step16 = (8u * row_bytes) >> 4;     // one 8-row swizzle group per tile row
             for (int j = 0; j < n_units; ++j) {
               const uint32_t a_lo = a_lo0 + stage * a_lo_stride + j * a_box16;
-              const uint32_t b_lo = b_lo0 + stage * b_lo_stride + j * 3 * b_tap16;
+              const uint32_t b_lo = p.b_res ? b_lo0 + (u0 + j) * 3 * b_tap16 : b_lo0 + stage * b_lo_stride + j * 3 * b_tap16;
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
                 for (int k = 0; k < ksteps; ++k) {
@@ -411,6 +448,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         acc_phase ^= 1u;
       }
     }
+    if (p.trace && lane == 0) {
+      p.trace[blockIdx.x * kTraceSlots + kTraceSlots - 2] = static_cast<unsigned long long>(w_full);
+      p.trace[blockIdx.x * kTraceSlots + kTraceSlots - 3] = static_cast<unsigned long long>(w_empty);
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: kEpiGroups column groups x 4 warps =====================
     const int ew = warp - 4;
@@ -420,13 +461,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;         // accumulator row = pixel within the tile
     const int gtid = (ew & 3) * 32 + lane; // thread index within the group
-    uint8_t* stage_c = smem_c + grp * kStageCBytes;   // this group's staging buffer
+    uint8_t* stage_c = smem_c + grp * p.stage_c;      // this group's staging buffer
     uint64_t* rbar = &res_bar[grp];
     float* bias_t = bias_s + team * 256;   // the team's bias copy (teams may be on different n-blocks)
     uint32_t res_phase = 0;
     const int chunks_total = (p.block_n + 31) >> 5;                  // 32-column chunks
     const int my_chunks = chunks_total > cg ? (chunks_total - cg + kEpiColGroups - 1) / kEpiColGroups : 0;
-    const int cps = p.out_f32 ? 1 : 2;                               // chunks per staging buffer (16 KiB)
+    const int cps = p.out_f32 ? 1 : (p.stage_c >> 13);               // chunks per staging buffer (8 / 16 KiB)
     const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
     const uint32_t c_chunk_stride = 128u * c_row_bytes;
     const uint32_t c_box_bytes = static_cast<uint32_t>(p.TW * p.TH) * c_row_bytes;
@@ -570,6 +611,11 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0 && p.span != nullptr) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    atomicMax(p.span + 1, gt);
+  }
   if (threadIdx.x == 0 && p.trace != nullptr) {
     trace_mark(p, 7);
     unsigned long long gt;
@@ -654,6 +700,10 @@ bool g_attr_set = false;
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
 const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
 unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace
+unsigned long long* g_span_buf = nullptr;    // cft_debug_conv_spans
+int g_span_next = 0, g_span_max = 0;
+const bool g_no_bres = getenv("CFT_NO_BRES") != nullptr;     // debug: never keep the weights resident
+const bool g_stage8k = getenv("CFT_STAGE8K") != nullptr;     // experiment: 8 KiB staging buffers for every bf16 output
 const bool g_no_pdl = getenv("CFT_NO_PDL") != nullptr;
 const bool g_no_halo = getenv("CFT_NO_ROW_REUSE") != nullptr;
 const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
@@ -748,14 +798,33 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   }
   p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
   p.trace = g_trace_buf;
-  const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * kStageCBytes;
+  p.span = nullptr;
+  if (g_span_buf != nullptr && g_span_next < g_span_max) p.span = g_span_buf + 2 * (g_span_next++);
+  p.out_f32 = a->out_dtype == CFT_DT_F32;
+  // epilogue staging: a 32-column chunk is 128 rows x 64 B (bf16) or x 128 B (f32); column groups that own a single
+  // bf16 chunk per tile get 8 KiB buffers, which leaves 32 KiB more for the operand ring
+  const int chunks_per_group = ((p.block_n + 31) / 32 + kEpiColGroups - 1) / kEpiColGroups;
+  p.stage_c = (!p.out_f32 && (chunks_per_group <= 1 || g_stage8k)) ? 8 * 1024 : kStageCBytes;
+  const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * p.stage_c;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;
   p.b_slot = p.halo ? ((p.ups * 3 * (p.block_n / ctas) * p.kelems * 2 + 1023) / 1024) * 1024 : (p.block_n / ctas) * 128;
+  // small weight matrices (3x3 convs up to 64 -> 64) stay resident in smem for the whole kernel: they were half of the
+  // L2 -> SM traffic of those layers, and TMA-latency x bytes-in-flight is what bounds them
+  p.b_res = 0;
+  p.b_res_bytes = 0;
+  if (p.halo && ctas == 1 && p.n_blocks == 1 && !g_no_bres) {
+    const int bytes = kw * p.kchunks * 3 * p.block_n * p.kelems * 2;
+    const int rounded = (bytes + 1023) / 1024 * 1024;
+    if (rounded <= 96 * 1024 && (ring_budget - rounded) / p.a_slot >= 3) {
+      p.b_res = rounded;
+      p.b_res_bytes = bytes;
+      p.b_slot = 0;
+    }
+  }
   const int stage_bytes = p.a_slot + p.b_slot;
-  p.stages = ring_budget / stage_bytes;
+  p.stages = (ring_budget - p.b_res) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   p.act = (a->act == CFT_ACT_SILU && g_silu_tanh) ? 3 : a->act;
-  p.out_f32 = a->out_dtype == CFT_DT_F32;
   p.ldy = a->ldy;
   p.y_coff = a->y_coff;
   p.ldr = a->ldr;
@@ -825,7 +894,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     }
   }
 
-  const int smem_bytes = 1024 + p.stages * stage_bytes + kEpiGroups * kStageCBytes + kTailBytes;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + p.b_res + kEpiGroups * p.stage_c + kTailBytes;
   if (!g_attr_set) {
     const int max_smem = kSmemTotal;
     rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
@@ -874,5 +943,14 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
 // cft_conv2d launch that follows (see trace_mark for the slot map); nullptr turns it off.  Not for production use.
 extern "C" int cft_debug_conv_trace(void* buf) {
   g_trace_buf = static_cast<unsigned long long*>(buf);
+  return CFT_OK;
+}
+
+// Debug: the next `max_launches` cft_conv2d launches (in issue order, also when captured into a CUDA graph) write
+// {first CTA start, last CTA end} (%globaltimer ns) into buf[2 * i], buf[2 * i + 1]; the caller presets {~0, 0}.
+extern "C" int cft_debug_conv_spans(void* buf, int max_launches) {
+  g_span_buf = static_cast<unsigned long long*>(buf);
+  g_span_next = 0;
+  g_span_max = buf ? max_launches : 0;
   return CFT_OK;
 }

@@ -10,7 +10,13 @@ CFT_NO_ROW_REUSE=1 TAILN=12 run conv_norowreuse python -m pytest tests/test_kern
 CFT_ATTENTION_SIMT=1 TAILN=6 run attn_simt python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attention" --tb=line
 TAILN=16 run model    python -m pytest tests/test_model_gpu.py -q -m gpu --tb=line -s
 TAILN=4 run smoke    python __graft_entry__.py smoke
+CFT_NO_BRES=1 TAILN=12 run conv_nobres python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv or gemm" --tb=line
+CFT_STAGE8K=1 TAILN=12 run conv_stage8k python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "conv or gemm" --tb=line
+TAILN=60 run step_1s  python scripts/trace_step.py 32 --one-stream
+TAILN=8 run step_2s  python scripts/trace_step.py 32
+CFT_STAGE8K=1 TAILN=60 run step_1s_stage8k  python scripts/trace_step.py 32 --one-stream
+if [ -n "$CI_FULL" ]; then
 TAILN=60 run layers   python scripts/profile_layers.py 32
 run shapes   python scripts/prof_shapes.py --time
-CFT_NO_ROW_REUSE=1 run shapes_norowreuse   python scripts/prof_shapes.py --time c3_p3_3x3_128 c3_p2_3x3_64
+fi
 run bench    python bench.py --steps 20 --warmup 5

@@ -62,10 +62,17 @@ def main():
             c = col(i)[t[:, i] != 0]
             if len(c):
                 print(f"   {lab:22s} min {c.min():7.2f}  median {c.median():7.2f}  max {c.max():7.2f} us   ({len(c)} CTAs)")
+        tot = (t[:, 7] - t[:, 1]).double()
+        for lab, i in (("MMA warp waiting for operands", SLOTS - 2), ("MMA warp waiting for a free accumulator", SLOTS - 3),
+                       ("producer waiting for a free ring slot", SLOTS - 4)):
+            c = t[:, i].double()
+            m = c > 0
+            if m.any():
+                print(f"   {lab:42s} median {float((c[m] / tot[m]).median()) * 100:5.1f} % of the CTA's lifetime")
         for cta in (0, 1, 2, n // 2, n - 1):
             row = t[cta]
             ev = []
-            for j in range((SLOTS - 10) // 2):
+            for j in range((SLOTS - 12) // 2):
                 if row[8 + 2 * j] or row[9 + 2 * j]:
                     ev.append(f"t{j}:{(int(row[8 + 2 * j]) - int(row[1])) / khz:.1f}-{(int(row[9 + 2 * j]) - int(row[1])) / khz:.1f}")
             print(f"   CTA {cta}: acc ready-released (us): " + " ".join(ev))
