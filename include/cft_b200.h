@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFT_ABI_VERSION 2
+#define CFT_ABI_VERSION 3
 
 enum {
   CFT_OK = 0,
@@ -92,6 +92,16 @@ int cft_conv2d_ref(const cft_conv_args* a, void* stream);
  * halves of the loader's [B,6,H,W] tensor, train.py:716-717). */
 int cft_focus_gather(const void* img, int in_dtype, int B, int H, int W, long long batch_stride,
                      int layout, void* y, void* stream);
+
+/* Fused Focus layer (models/common.py:168-180 = space-to-depth + concat + Conv 3x3 + BN + SiLU) straight from the
+ * loader's uint8 image (utils/datasets.py:1272-1281; the 1/255 of train.py:715 / test.py:107-108 is applied to the
+ * fp32 accumulator).  img: uint8 [B,3,H,W] (H, W even, W % 16 == 0, batch_stride bytes between images: 6*H*W for the
+ * halves of the [B,6,H,W] loader tensor).  w: fp16 [Cout][192], the 3x3x12 filter re-indexed as a 6x6 stride-2 filter
+ * on the image: w[o][(c*6 + r)*8 + q] = W[o][(gy + 2*gx)*3 + c][ky][kx] with r = 2*ky + gy, q = 2*kx + gx (q = 6, 7 and
+ * columns >= 144 are zero); BN is folded in before the fp16 rounding.  y: NHWC bf16 [B,H/2,W/2,ldy] channel slice.
+ * Cout: multiple of 16, <= 128.  act: CFT_ACT_NONE or CFT_ACT_SILU. */
+int cft_focus_conv(const void* img, int B, int H, int W, long long batch_stride, const void* w, const float* bias,
+                   int Cout, int act, void* y, int ldy, int y_coff, void* stream);
 
 /* MaxPool k x k, stride 1, pad k/2 (-inf padding) on an NHWC bf16 channel slice
  * (SPP, models/common.py:160-165).  src/dst may be slices of the same buffer. */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "cft_debug_conv_trace": ([_P], _I),
     "cft_debug_conv_spans": ([_P, _I], _I),
     "cft_focus_gather": ([_P, _I, _I, _I, _I, _LL, _I, _P, _P], _I),
+    "cft_focus_conv": ([_P, _I, _I, _I, _LL, _P, _P, _I, _I, _P, _I, _I, _P], _I),
     "cft_maxpool_s1": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_maxpool_cascade3": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "cft_upsample2x": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P], _I),

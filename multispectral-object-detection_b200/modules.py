@@ -13,6 +13,7 @@ Activations between modules: logical NCHW, physical NHWC (channels_last) bf16.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -92,10 +93,12 @@ class Conv(nn.Module):
 
 
 class Focus(nn.Module):
-    """reference models/common.py:168-180: space-to-depth gather kernel (16 channels, 12 used; reads the loader's
-    uint8 wire format directly) + 3x3 tcgen05 conv in row-reuse mode (three 18x8-pixel boxes per tile).
-    ``wide = True`` selects the alternative x-direction-im2col layout (64 channels) + 3x1 conv."""
+    """reference models/common.py:168-180.  uint8 images (the loader's wire format) take the FUSED kernel: space-to-depth
+    + 3x3 conv + BN + SiLU as one 6x6 stride-2 tcgen05 conv on the raw image (``cft_focus_conv``).  fp32 / bf16 images
+    (already scaled to [0,1]) take the two-kernel path: space-to-depth gather (16 channels, 12 used) + 3x3 conv in
+    row-reuse mode; ``wide = True`` selects the x-direction-im2col layout (64 channels) + 3x1 conv for that path."""
     wide = False
+    fused = os.environ.get("CFT_NO_FUSED_FOCUS") is None
 
     def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
         super().__init__()
@@ -121,6 +124,13 @@ class Focus(nn.Module):
                 w3[:, :, :48] = w.view(co, 3, 3, 16).reshape(co, 3, 48)
                 w = w3.contiguous()
             return w, b
+        cout = cv.conv.out_channels
+        if self.fused and k == 3 and s == 1 and cout % 16 == 0 and ops.focus_conv_supported(x, cout, act):
+            def build_fused():
+                bnp = (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None else None
+                return ops.pack_focus_weight(cv.conv.weight, cv.conv.bias, bnp, device=x.device)
+            wf, bf = self._packed.get((_versions(*srcs), str(x.device), "fused"), build_fused)
+            return ops.focus_conv(x, wf, bf, cout, act, out=out)
         w, b = self._packed.get((_versions(*srcs), str(x.device), wide), build)
         if wide:
             g = ops.focus_gather(x, layout=1)

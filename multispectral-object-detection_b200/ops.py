@@ -184,6 +184,61 @@ def focus_gather(img: torch.Tensor, layout: int = 0) -> torch.Tensor:
     return y
 
 
+def pack_focus_weight(w: torch.Tensor, bias: Optional[torch.Tensor], bn=None, device=None):
+    """Focus conv weight [Cout, 12, 3, 3] (+ BatchNorm to fold) -> (fp16 [Cout_p][192], fp32 bias [Cout_p]) for
+    ``focus_conv``: the 3x3 filter over the 12 space-to-depth channels (channel (gy + 2 gx) * 3 + c,
+    models/common.py:179) re-indexed as a 6x6 stride-2 filter on the image, K = ((c * 6 + r) * 8 + q) with r = 2 ky + gy,
+    q = 2 kx + gx; q = 6, 7 and K >= 144 are zero padding.  Cout is padded to a multiple of 16."""
+    w = w.detach().float()
+    cout, cin, kh, kw = w.shape
+    if cin != 12 or kh != 3 or kw != 3:
+        raise _lib.CftError(f"pack_focus_weight expects a [Cout,12,3,3] weight, got {tuple(w.shape)}")
+    b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        scale = gamma.detach().float() / torch.sqrt(var.detach().float() + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - mean.detach().float()) * scale + beta.detach().float()
+    cout_p = (cout + 15) // 16 * 16
+    w6 = w.view(cout, 2, 2, 3, 3, 3)                       # [o, gx, gy, c, ky, kx]  (group g = gy + 2 gx)
+    w6 = w6.permute(0, 3, 4, 2, 5, 1)                      # [o, c, ky, gy, kx, gx]
+    w6 = w6.reshape(cout, 3, 6, 6)                         # [o, c, r = 2 ky + gy, q = 2 kx + gx]
+    packed = torch.zeros(cout_p, 24, 8, dtype=torch.float32, device=w.device)
+    packed[:cout, :18, :6] = w6.reshape(cout, 18, 6)
+    bias_p = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
+    bias_p[:cout] = b
+    dev = device if device is not None else w.device
+    return packed.view(cout_p, 192).to(device=dev, dtype=torch.float16).contiguous(), bias_p.to(dev).contiguous()
+
+
+def focus_conv_supported(img: torch.Tensor, cout: int, act: int) -> bool:
+    """The fused kernel reads the loader's uint8 image through TMA: 16-byte aligned rows and image planes."""
+    if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[1] != 3:
+        return False
+    b, _, h, w = img.shape
+    ok_layout = img.stride(3) == 1 and img.stride(2) == w and img.stride(1) == h * w and (b == 1 or img.stride(0) % 16 == 0)
+    return (ok_layout and h % 2 == 0 and w % 16 == 0 and (h * w) % 16 == 0 and img.data_ptr() % 16 == 0 and cout <= 128
+            and act in (_lib.ACT_NONE, _lib.ACT_SILU))
+
+
+def focus_conv(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, cout: int, act: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused Focus (space-to-depth + 3x3 conv + bias + SiLU) from the uint8 image [B,3,H,W] (a view of the loader's
+    [B,6,H,W] tensor is fine) to NHWC bf16 [B,cout,H/2,W/2]; ``w, bias`` from ``pack_focus_weight``."""
+    lib = _lib.lib()
+    _require_cuda(img, "image")
+    if not focus_conv_supported(img, cout, act):
+        raise _lib.CftError("focus_conv: unsupported image layout / width / activation (use focus_gather + conv2d)")
+    b, _, h, wd = img.shape
+    if out is None:
+        out = empty_nhwc(b, cout, h // 2, wd // 2, img.device)
+    yp, ldy = nhwc_desc(out)
+    bstride = img.stride(0) if b > 1 else 3 * h * wd
+    _lib.check(lib.cft_focus_conv(img.data_ptr(), b, h, wd, bstride, w.data_ptr(), bias.data_ptr(), w.shape[0], act,
+                                  yp, ldy, 0, _stream()), "cft_focus_conv")
+    return out
+
+
 def maxpool_s1(x: torch.Tensor, out: torch.Tensor, k: int) -> torch.Tensor:
     lib = _lib.lib()
     xp, ldx = nhwc_desc(x)

@@ -60,7 +60,7 @@ def test_c_abi_exports_every_declared_symbol(cft):
     for name in declared:
         assert hasattr(lib, name), f"libcft_b200.so does not export {name}"
     assert set(cft._lib.SIGNATURES) == declared
-    assert lib.cft_abi_version() == 2
+    assert lib.cft_abi_version() == 3
 
 
 def test_forward_fails_loudly_without_cuda(cft):
@@ -113,3 +113,23 @@ def test_install_and_convert_into_reference(cft, oracle):
     sd3 = rm3.state_dict()
     assert set(sd3) == set(sd) and all(torch.equal(sd3[k], sd[k]) for k in sd)
     assert all(type(m).__module__ == "multispectral-object-detection_b200.modules" for m in rm3.model)
+
+
+def test_focus_weight_reindexing_is_a_6x6_stride2_conv(cft):
+    """pack_focus_weight: Focus (space-to-depth + 3x3 / pad 1, models/common.py:168-180) == 6x6 / stride 2 / pad 2 conv
+    on the image with the re-indexed filter (the identity the fused CUDA kernel is built on), checked in fp64 on CPU."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(16, 12, 3, 3, generator=g)
+    b = torch.randn(16, generator=g)
+    x = torch.rand(2, 3, 20, 28, generator=g)
+    s2d = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)
+    ref = F.conv2d(s2d.double(), w.double(), b.double(), padding=1)
+    wf, bf = cft.ops.pack_focus_weight(w, b, None, device="cpu")
+    assert wf.shape == (16, 192) and wf.dtype == torch.float16 and torch.equal(bf, b)
+    w6 = wf.float().view(16, 24, 8)
+    assert (w6[:, 18:] == 0).all() and (w6[:, :, 6:] == 0).all()
+    k66 = w.view(16, 2, 2, 3, 3, 3).permute(0, 3, 4, 2, 5, 1).reshape(16, 3, 6, 6)      # exact (unrounded) 6x6 filter
+    assert torch.allclose(w6[:, :18, :6].reshape(16, 3, 6, 6), k66, atol=2e-3, rtol=1e-3)   # fp16 rounding only
+    y = F.conv2d(x.double(), k66.double(), b.double(), stride=2, padding=2)
+    assert y.shape == ref.shape and torch.allclose(y, ref, atol=1e-12)

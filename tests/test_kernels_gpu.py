@@ -183,6 +183,61 @@ def test_focus_module_matches_torch(wide, cft):
     close_bf16(y, ref, "Focus module")
 
 
+def _focus_reference(img_u8, conv_w, bn, bias=None):
+    """reference Focus on the loader's bytes: x = img / 255 (test.py:107-108), space-to-depth, conv 3x3, BN, SiLU."""
+    x = img_u8.float() / 255.0
+    s2d = torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1)      # common.py:179
+    y = F.conv2d(s2d, conv_w, bias, padding=1)
+    if bn is not None:
+        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0., bn.eps)
+    return y
+
+
+@pytest.mark.parametrize("B,Cout,H,W", [(2, 64, 64, 96), (1, 32, 32, 32), (2, 80, 48, 80), (3, 64, 80, 112), (1, 128, 16, 16)])
+def test_focus_conv_fused_matches_reference(B, Cout, H, W, cft):
+    """cft_focus_conv (uint8 image -> 6x6 stride-2 tcgen05 conv, fp16 operands) == SiLU(BN(conv3x3(space_to_depth(x/255)))).
+    Tolerance: fp16 weights (2^-11 relative) on exactly represented pixels, bf16 output rounding (2^-9)."""
+    torch.manual_seed(Cout + H)
+    m = cft.Focus(3, Cout, 3).eval()
+    m.conv.bn.eps = 1e-3
+    with torch.no_grad():
+        m.conv.bn.running_mean.normal_(0, .1); m.conv.bn.running_var.uniform_(.5, 1.5)
+        m.conv.bn.weight.uniform_(.5, 1.5); m.conv.bn.bias.normal_(0, .1)
+    m = m.to(DEV)
+    # the RGB and IR halves of the loader's [B,6,H,W] tensor are consumed in place (batch stride 6*H*W)
+    x6 = torch.randint(0, 256, (B, 6, H, W), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).to(DEV)
+    for half in (x6[:, :3], x6[:, 3:]):
+        assert cft.ops.focus_conv_supported(half, Cout, 1)
+        with torch.no_grad():
+            y = m(half)
+            ref = F.silu(_focus_reference(half, m.conv.conv.weight, m.conv.bn))
+        torch.cuda.synchronize()
+        assert y.shape == (B, Cout, H // 2, W // 2)
+        d = (y.float() - ref).abs()
+        tol = 2e-3 + 6e-3 * ref.abs()
+        assert (d <= tol).all(), f"fused Focus: max |d| {d.max().item():.4g}, worst excess {(d - tol).max().item():.4g}"
+
+
+def test_focus_conv_fused_vs_two_kernel_path_and_no_act(cft):
+    """Fused and gather+conv paths agree (the fused one is the more accurate: no bf16 rounding of x/255); act = none."""
+    ops = cft.ops
+    w = rnd(64, 12, 3, 3, seed=2, scale=1.0 / math.sqrt(108)).cpu()
+    b = rnd(64, seed=3, scale=0.5).cpu()
+    img = torch.randint(0, 256, (2, 3, 64, 64), dtype=torch.uint8, generator=torch.Generator().manual_seed(7)).to(DEV)
+    wf, bf = ops.pack_focus_weight(w, b, None, device=DEV)
+    assert wf.shape == (64, 192) and wf.dtype == torch.float16
+    y = ops.focus_conv(img, wf, bf, 64, 0)
+    wp, bp = ops.pack_conv_weight(w, b, None, cin_pad_to=16, device=DEV)
+    y2 = ops.conv2d(ops.focus_gather(img), wp, bp, 3, 1, 0, cout=64, cin=16)
+    ref = _focus_reference(img, w.to(DEV), None, b.to(DEV))
+    torch.cuda.synchronize()
+    e_fused = (y.float() - ref).abs().max().item()
+    e_two = (y2.float() - ref).abs().max().item()
+    assert e_fused <= 2e-3 + 6e-3 * ref.abs().max().item(), e_fused
+    assert e_fused <= e_two + 1e-3, (e_fused, e_two)
+    close_bf16(y2, ref, "two-kernel Focus")
+
+
 def test_maxpool_cascade_equals_5_9_13(cft):
     ops = cft.ops
     x = nhwc(rnd(2, 64, 20, 20, seed=3))
