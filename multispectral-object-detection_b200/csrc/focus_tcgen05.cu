@@ -12,7 +12,7 @@
 //               converted to fp16 EXACTLY (PRMT to 0x64xx = 1024 + x, minus 1024), so the only rounding of this layer
 //               is that of the fp16 weights; 1/255 is applied to the fp32 accumulator.
 //   warp 1      9 tcgen05.mma (kind::f16, fp16 x fp16 -> fp32 in TMEM) per tile, weights resident in smem
-//   warps 12-15 epilogue: tcgen05.ld -> acc / 255 + bias -> SiLU -> bf16 -> swizzled staging -> TMA store (NHWC slice)
+//   warps 12-19 epilogue: tcgen05.ld -> acc / 255 + bias -> SiLU -> bf16 -> swizzled staging -> TMA store (NHWC slice)
 // Replaces cft_focus_gather + the 16-channel cft_conv2d whose 32-byte operand rows ran at 14 % of the tensor peak.
 #include <cuda_fp16.h>
 
@@ -24,15 +24,16 @@ namespace {
 
 using namespace cft::ptx;
 
-constexpr int kFThreads = 512;
+constexpr int kFThreads = 640;
+constexpr int kFEpiWarps = 8;             // warps 12..19: two per TMEM lane quarter, alternating 32-column chunks
 constexpr int kFBuilderWarps = 8;         // warps 4..11
 constexpr int kFTileW = 16, kFTileH = 8;  // output pixels per tile (128 = one UMMA M)
 constexpr int kFPatchW = 64, kFPatchH = 20;                 // image bytes [2 x0 - 16, 2 x0 + 48) x [2 y0 - 2, 2 y0 + 18): the
                                                             // 36 needed columns start at byte 14 (TMA boxes start on 16 B)
 constexpr int kFPatchX0 = 14;
 constexpr int kFPatchBytes = kFPatchW * kFPatchH * 3;       // 3840
-constexpr int kFPatchSlot = 4096;
-constexpr int kFPatches = 4;
+constexpr int kFPatchSlot = 3840;                           // 128 B aligned
+constexpr int kFMaxPatches = 6;                             // TMA latency / 6 in flight stays below the per-tile time
 constexpr int kFMaxAStages = 3;
 constexpr int kFAtomBytes = 128 * 128;                      // 128 rows x 64 fp16
 constexpr int kFATileBytes = 3 * kFAtomBytes;               // K = 144 -> atoms 0, 1 full, atom 2: one 16-element step
@@ -43,7 +44,7 @@ constexpr int kFAccStages = 4;                              // 4 x 128 TMEM colu
 struct FocusMaps {
   CUtensorMap img;   // uint8 (W, H, 3, B), box (64, 20, 3, 1), no swizzle
   CUtensorMap w;     // fp16 [Cout][192], box (64, Cout), SWIZZLE_128B
-  CUtensorMap c;     // bf16 out (Cout, Wo, Ho, B), box (32, 16, 8, 1), SWIZZLE_64B
+  CUtensorMap c;     // bf16 out (Cout, Wo, Ho, B), box (32, 16, 2, 1), SWIZZLE_64B
 };
 
 struct FocusParams {
@@ -51,6 +52,8 @@ struct FocusParams {
   int tiles_x, tiles_y, num_tiles;
   int act;              // CFT_ACT_NONE / CFT_ACT_SILU
   int chunks;           // ceil(Cout / 32)
+  int dbg;              // timing experiments only (CFT_FOCUS_DEBUG): 1 = builders idle, 2 = epilogue idle, 4 = no MMA
+  int patches;          // image-patch ring depth (<= kFMaxPatches)
   int a_stages;         // A-tile ring depth (3, or 2 when the weights / staging of a wide layer need the room)
   const float* bias;
 };
@@ -73,11 +76,11 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
   uint8_t* smem_a = smem;                                              // [a_stages][3 atoms][128 rows][128 B]
   uint8_t* smem_w = smem_a + p.a_stages * kFATileBytes;                // [3 atoms][Cout rows][128 B]
   uint8_t* smem_c = smem_w + 3 * p.Cout * 128;                         // [2][chunks][8 KiB]
-  uint8_t* smem_p = smem_c + 2 * p.chunks * kFStageC;                  // [kFPatches][3072]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + kFPatches * kFPatchSlot);
-  uint64_t* pfull = bars;                    // [kFPatches]  TMA -> builders
-  uint64_t* pempty = bars + kFPatches;       // [kFPatches]  builders -> TMA
-  uint64_t* afull = bars + 2 * kFPatches;    // [kFMaxAStages]  builders -> MMA
+  uint8_t* smem_p = smem_c + 2 * p.chunks * kFStageC;                  // [kFMaxPatches][3072]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + p.patches * kFPatchSlot);
+  uint64_t* pfull = bars;                    // [kFMaxPatches]  TMA -> builders
+  uint64_t* pempty = bars + kFMaxPatches;       // [kFMaxPatches]  builders -> TMA
+  uint64_t* afull = bars + 2 * kFMaxPatches;    // [kFMaxAStages]  builders -> MMA
   uint64_t* aempty = afull + kFMaxAStages;      // [kFMaxAStages]  MMA -> builders
   uint64_t* tfull = aempty + kFMaxAStages;      // [kFAccStages] MMA -> epilogue
   uint64_t* tempty = tfull + kFAccStages;    // [kFAccStages] epilogue -> MMA
@@ -89,7 +92,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
     prefetch_tmap(&maps.img);
     prefetch_tmap(&maps.w);
     prefetch_tmap(&maps.c);
-    for (int i = 0; i < kFPatches; ++i) {
+    for (int i = 0; i < kFMaxPatches; ++i) {
       mbar_init(&pfull[i], 1);
       mbar_init(&pempty[i], kFBuilderWarps);
     }
@@ -99,7 +102,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
     }
     for (int i = 0; i < kFAccStages; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kFEpiWarps);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -142,7 +145,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
         tma_load_4d(smem_p + slot * kFPatchSlot, &maps.img, &pfull[slot], 2 * x0 - 2 - kFPatchX0, 2 * y0 - 2, 0, b);
       }
       __syncwarp();
-      if (++slot == kFPatches) {
+      if (++slot == p.patches) {
         slot = 0;
         phase ^= 1u;
       }
@@ -165,7 +168,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 128);
         const uint32_t a_lo = a_lo0 + stage * (kFATileBytes >> 4);
 #pragma unroll
-        for (int s = 0; s < 9; ++s) {            // K steps of 16: atoms 0, 1 hold four each, atom 2 the last one
+        for (int s = 0; s < ((p.dbg & 4) ? 1 : 9); ++s) {            // K steps of 16: atoms 0, 1 hold four each, atom 2 the last one
           const uint32_t atom = s >> 2, k = s & 3;
           const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + atom * (kFAtomBytes >> 4) + 2 * k);
           const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (w_lo0 + atom * w_atom16 + 2 * k);
@@ -205,6 +208,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       mbar_wait(&pfull[slot], pphase);
       const uint8_t* patch = smem_p + slot * kFPatchSlot;
       uint8_t* a_tile = smem_a + stage * kFATileBytes;
+      if (!(p.dbg & 1))
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -236,7 +240,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
         mbar_arrive(&afull[stage]);
         mbar_arrive(&pempty[slot]);
       }
-      if (++slot == kFPatches) {
+      if (++slot == p.patches) {
         slot = 0;
         pphase ^= 1u;
       }
@@ -246,10 +250,10 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       }
     }
   } else if (warp >= 12) {
-    // ===================== epilogue (4 warps = the 4 TMEM lane quarters) =====================
+    // ===================== epilogue (8 warps: lane quarter = warp % 4, chunk parity = (warp - 12) / 4) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - 384;
+    const int cg = (warp - 12) >> 2;
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
     const float scale = p.act == CFT_ACT_SILU ? 0.5f / 255.f : 1.f / 255.f;
@@ -257,12 +261,12 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       int b, y0, x0;
       decode(tile, b, y0, x0);
       uint8_t* stage_c = smem_c + buf * p.chunks * kFStageC;
-      if (etid == 0) bulk_wait_read<1>();        // the store that last used this buffer has drained it
-      named_bar_sync(1, 128);
+      if (lane == 0) bulk_wait_read<1>();        // this warp's store that last used the buffer has drained it
+      __syncwarp();
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 128);
-      for (int ch = 0; ch < p.chunks; ++ch) {
+      for (int ch = cg; ch < ((p.dbg & 2) ? 0 : p.chunks); ch += 2) {
         uint32_t v[32];
         tmem_ld32(t_row + static_cast<uint32_t>(ch * 32), v);
         float f[32];
@@ -295,9 +299,11 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (etid == 0) {
-        for (int ch = 0; ch < p.chunks; ++ch) tma_store_4d(&maps.c, stage_c + ch * kFStageC, ch * 32, x0, y0, b);
+      __syncwarp();
+      // every warp stores its own 32 accumulator rows = two 16-pixel rows of the tile: no cross-warp barrier in the loop
+      if (lane == 0 && !(p.dbg & 2)) {
+        for (int ch = cg; ch < p.chunks; ch += 2)
+          tma_store_4d(&maps.c, stage_c + ch * kFStageC + q * 2048, ch * 32, x0, y0 + 2 * q, b);
         bulk_commit();
       }
       buf ^= 1;
@@ -306,7 +312,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
         acc_phase ^= 1u;
       }
     }
-    if (etid == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -375,6 +381,7 @@ extern "C" int cft_focus_conv(const void* img, int B, int H, int W, long long ba
   p.act = act;
   p.chunks = (Cout + 31) / 32;
   p.bias = bias;
+  p.dbg = getenv("CFT_FOCUS_DEBUG") ? atoi(getenv("CFT_FOCUS_DEBUG")) : 0;
 
   FocusMaps maps;
   int rc;
@@ -396,14 +403,23 @@ extern "C" int cft_focus_conv(const void* img, int B, int H, int W, long long ba
     const uint8_t* yb = reinterpret_cast<const uint8_t*>(y) + static_cast<size_t>(y_coff) * 2;
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)p.Wo * ldy * 2, (cuuint64_t)p.Ho * p.Wo * ldy * 2};
-    cuuint32_t box[4] = {32, kFTileW, kFTileH, 1};
+    cuuint32_t box[4] = {32, kFTileW, 2, 1};        // one epilogue warp's share of a tile: 32 pixels = 2 rows
     rc = encode(&maps.c, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, yb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
 
-  const int fixed = 1024 + 3 * Cout * 128 + 2 * p.chunks * kFStageC + kFPatches * kFPatchSlot + 256 + kFMaxCout * 4;
-  p.a_stages = (fixed + kFMaxAStages * kFATileBytes <= 227 * 1024) ? kFMaxAStages : 2;
-  const int smem_bytes = fixed + p.a_stages * kFATileBytes;
+  p.patches = kFMaxPatches;
+  p.a_stages = kFMaxAStages;
+  auto smem_need = [&]() {
+    return 1024 + p.a_stages * kFATileBytes + 3 * Cout * 128 + 2 * p.chunks * kFStageC + p.patches * kFPatchSlot + 256 + kFMaxCout * 4;
+  };
+  while (smem_need() > 227 * 1024) {        // wide layers: give up ring depth for their weights and staging
+    if (p.a_stages > 2) --p.a_stages;
+    else if (p.patches > 3) --p.patches;
+    else break;
+  }
+  const int smem_bytes = smem_need();
+  CFT_REQUIRE(smem_bytes <= 227 * 1024, "cft_focus_conv: shared memory budget exceeded (Cout %d)", Cout);
   if (!g_focus_attr) {
     rc = check_cuda(cudaFuncSetAttribute(cft_focus_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                     "cudaFuncSetAttribute(focus_tcgen05)");
