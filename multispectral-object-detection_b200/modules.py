@@ -104,6 +104,7 @@ class Focus(nn.Module):
         super().__init__()
         self.conv = Conv(c1 * 4, c2, k, s, p, g, act)
         self._packed = _Packed()
+        self._packed_fused = _Packed()     # separate caches: a captured CUDA graph keeps pointing at the tensors of its path
 
     def forward(self, x, out=None):
         if x.shape[1] != 3:
@@ -129,7 +130,7 @@ class Focus(nn.Module):
             def build_fused():
                 bnp = (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None else None
                 return ops.pack_focus_weight(cv.conv.weight, cv.conv.bias, bnp, device=x.device)
-            wf, bf = self._packed.get((_versions(*srcs), str(x.device), "fused"), build_fused)
+            wf, bf = self._packed_fused.get((_versions(*srcs), str(x.device)), build_fused)
             return ops.focus_conv(x, wf, bf, cout, act, out=out)
         w, b = self._packed.get((_versions(*srcs), str(x.device), wide), build)
         if wide:
