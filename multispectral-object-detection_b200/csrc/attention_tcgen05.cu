@@ -60,6 +60,9 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;          // S: columns [0,128)
   const uint32_t tmem_o = tmem_base + 128;    // O: columns [128,128+dk)
+  // barrier init / TMEM allocation above overlap the tail of the QKV GEMM; its output is read from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (tid == 0) {
     mbar_arrive_expect_tx(tma_bar, 3u * static_cast<uint32_t>(tile_bytes));
@@ -221,7 +224,7 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
   }
   dim3 grid(heads, B);
   LaunchScope ls(CFT_K_ATTENTION, stream);
-  cft_attention_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(map, p);
+  cft::launch(cft_attention_tcgen05_kernel, dim3(grid), dim3(kThreads), smem, stream, map, p);
   return ls.finish("cft_attention (tcgen05) launch");
 }
 }  // namespace cft

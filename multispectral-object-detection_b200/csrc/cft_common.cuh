@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/cft_b200.h"
 
@@ -27,6 +28,30 @@ struct LaunchScope {
 
 int sm_count();
 
+// Programmatic dependent launch for the small kernels as well (CFT_PDL_ALL=1; default: plain stream order): every kernel of
+// the library starts with pdl_prologue(), so a kernel may be scheduled while its predecessor drains and only its
+// launch latency -- never a memory access -- overlaps the predecessor.
+bool pdl_all();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (pdl_all()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // attention_tcgen05.cu: CFT_E_UNSUPPORTED when the shape is outside the tensor-core kernel.
 int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads, cudaStream_t stream);
 
@@ -36,6 +61,12 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
   } while (0)
 
 // ---------------------------------------------------------------- device helpers
+// First statement of every small kernel: let the next kernel in the stream begin launching, then wait until all
+// predecessor kernels have completed and their writes are visible (both are no-ops for a plain launch).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 // SiLU on the SFU: x * rcp(1 + 2^(-x*log2e)); 2 MUFU + 3 FP32 ops, relative error ~1e-6 (far below bf16's 2^-9).
 __device__ __forceinline__ float silu_fast(float v) {
@@ -57,6 +88,21 @@ __device__ __forceinline__ float silu_tanh_h(float h) {   // h = v / 2 already f
   return fmaf(h, t, h);
 }
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|err| <= 1.5e-7), written through erfc so that the negative tail
+// has no cancellation: q = erfc(|v|/sqrt2)/2, gelu = v - v*q (v >= 0) or v*q (v < 0).  2 SFU ops + ~10 FP32 ops per
+// element (erff: ~30); abs error vs the exact erf form <= 4e-7, far below the bf16 rounding of the result.
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float ax = fabsf(v) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float q = poly * t * e;
+  return v >= 0.f ? fmaf(-v, q, v) : v * q;
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == CFT_ACT_SILU) return silu_f(v);
   if (act == CFT_ACT_GELU) return gelu_f(v);

@@ -545,6 +545,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
             if (p.act == CFT_ACT_SILU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = silu_fast(f[i]);
+            } else if (p.act == 4) {          // erf-GELU, A&S erf (host: CFT_GELU_FAST)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
             } else if (p.act == CFT_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
@@ -698,6 +701,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
+const bool g_gelu_fast = getenv("CFT_GELU_FAST") != nullptr;   // 2-SFU-op erf-GELU instead of erff
 const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
 unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace
 unsigned long long* g_span_buf = nullptr;    // cft_debug_conv_spans
@@ -824,7 +828,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   const int stage_bytes = p.a_slot + p.b_slot;
   p.stages = (ring_budget - p.b_res) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  p.act = (a->act == CFT_ACT_SILU && g_silu_tanh) ? 3 : a->act;
+  p.act = (a->act == CFT_ACT_SILU && g_silu_tanh) ? 3 : ((a->act == CFT_ACT_GELU && g_gelu_fast) ? 4 : a->act);
   p.ldy = a->ldy;
   p.y_coff = a->y_coff;
   p.ldr = a->ldr;

@@ -15,6 +15,7 @@ using namespace cft;
 __global__ void __launch_bounds__(256)
 pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb, const __nv_bfloat16* __restrict__ ir, int ld_ir,
                    int H, int W, int C, int va, int ha, const float* __restrict__ pos, float* __restrict__ tok) {
+  pdl_prologue();
   // 256 threads = (C/8 channel vectors) x (pixel slices): every thread accumulates its slice of the bin, slices are
   // combined through smem.  All 256 threads stay busy for any C (the per-token kernel used C/8 of 128 threads).
   __shared__ float red[256 * 8];
@@ -63,6 +64,7 @@ pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb, const __nv
 template <bool kOutF32>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                  const float* __restrict__ be, float eps, long long rows, int C, void* __restrict__ y) {
+  pdl_prologue();
   // one warp per row; the row is read from global memory once and kept in registers (C <= 2048)
   constexpr int kMaxV = 16;                       // float4 per lane (C <= 2048)
   const int lane = threadIdx.x & 31;
@@ -121,6 +123,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // smem fp32.  softmax in fp32 with the 1/sqrt(dk) scale folded into the exponent.
 __global__ void __launch_bounds__(128)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int C, int heads) {
+  pdl_prologue();
   extern __shared__ uint8_t sm[];
   const int dk = C / heads;
   const int ldp = dk + 2;
@@ -218,6 +221,7 @@ __device__ __forceinline__ void bilin(int dst, int in, int out, int* i0, int* i1
 }
 
 __global__ void unpool_kernel(UnpoolArgs a) {
+  pdl_prologue();
   const int C8 = a.C / 8;
   const int cells = a.va * a.ha;
   const long long total = static_cast<long long>(a.B) * a.H * a.W * C8;
@@ -274,6 +278,7 @@ __global__ void unpool_kernel(UnpoolArgs a) {
 // coalesced, and the token tensor is read ~H/va times less often than by the per-pixel kernel.
 constexpr int kUnpoolCC = 64;
 __global__ void unpool_rows_kernel(UnpoolArgs a) {
+  pdl_prologue();
   extern __shared__ float srow[];                 // [2][ha][kUnpoolCC]
   const int y = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
   const int cells = a.va * a.ha;
@@ -342,6 +347,7 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
 __global__ void detect_decode_kernel(const float* __restrict__ head, int ldh, int B, int ny, int nx, int na, int no,
                                      float stride, const float* __restrict__ anchors, float* __restrict__ raw,
                                      float* __restrict__ z, long long z_rows, long long z_row0) {
+  pdl_prologue();
   const long long total = static_cast<long long>(B) * na * ny * nx;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -401,7 +407,7 @@ extern "C" int cft_gpt_pool_tokens(const void* rgb, int ld_rgb, int coff_rgb, co
   CFT_REQUIRE(B > 0 && H >= 1 && W >= 1 && va >= 1 && ha >= 1 && B <= 65535, "cft_gpt_pool_tokens: bad shape");
   dim3 grid(2 * va * ha, B);
   LaunchScope ls(CFT_K_POOL_TOKENS, stream);
-  pool_tokens_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(rgb) + coff_rgb, ld_rgb,
+  cft::launch(pool_tokens_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(rgb) + coff_rgb, ld_rgb,
                                                reinterpret_cast<const __nv_bfloat16*>(ir) + coff_ir, ld_ir, H, W, C, va,
                                                ha, pos_emb, tokens);
   return ls.finish("cft_gpt_pool_tokens launch");
@@ -416,9 +422,9 @@ extern "C" int cft_layernorm(const float* x, const float* gamma, const float* be
   const long long blocks = (rows + warps - 1) / warps;
   LaunchScope ls(CFT_K_LAYERNORM, stream);
   if (out_dtype == CFT_DT_F32)
-    layernorm_kernel<true><<<static_cast<unsigned>(blocks), warps * 32, 0, stream>>>(x, gamma, beta, eps, rows, C, y);
+    cft::launch(layernorm_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream, x, gamma, beta, eps, rows, C, y);
   else if (out_dtype == CFT_DT_BF16)
-    layernorm_kernel<false><<<static_cast<unsigned>(blocks), warps * 32, 0, stream>>>(x, gamma, beta, eps, rows, C, y);
+    cft::launch(layernorm_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream, x, gamma, beta, eps, rows, C, y);
   else
     return fail_arg("cft_layernorm: bad out_dtype");
   return ls.finish("cft_layernorm launch");
@@ -445,7 +451,7 @@ extern "C" int cft_attention(const void* qkv, void* out, int B, int T, int C, in
   }
   dim3 grid(heads, B);
   LaunchScope ls(CFT_K_ATTENTION, stream);
-  attention_kernel<<<grid, 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+  cft::launch(attention_kernel, dim3(grid), dim3(128), smem, stream, reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                 reinterpret_cast<__nv_bfloat16*>(out), T, C, heads);
   return ls.finish("cft_attention launch");
 }
@@ -476,10 +482,10 @@ extern "C" int cft_gpt_unpool(const float* tok, int B, int H, int W, int C, int 
     int threads = W * (kUnpoolCC / 8);
     threads = threads > 512 ? 512 : (threads < 64 ? 64 : (threads + 31) / 32 * 32);
     dim3 grid(H, chunks, B);
-    unpool_rows_kernel<<<grid, threads, 2 * ha * kUnpoolCC * sizeof(float), stream>>>(a);
+    cft::launch(unpool_rows_kernel, dim3(grid), dim3(threads), 2 * ha * kUnpoolCC * sizeof(float), stream, a);
   } else {
     const long long total = static_cast<long long>(B) * H * W * (C / 8);
-    unpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+    cft::launch(unpool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, a);
   }
   return ls.finish("cft_gpt_unpool launch");
 }
@@ -493,7 +499,7 @@ extern "C" int cft_detect_decode(const float* head, int ldh, int B, int ny, int 
   CFT_REQUIRE(z_row0 >= 0 && z_row0 + static_cast<long long>(na) * ny * nx <= z_rows, "cft_detect_decode: z rows out of range");
   const long long total = static_cast<long long>(B) * na * ny * nx;
   LaunchScope ls(CFT_K_DETECT, stream);
-  detect_decode_kernel<<<grid_for(total, 128), 128, 0, stream>>>(head, ldh, B, ny, nx, na, no, stride, anchors_px, raw,
+  cft::launch(detect_decode_kernel, dim3(grid_for(total, 128)), dim3(128), 0, stream, head, ldh, B, ny, nx, na, no, stride, anchors_px, raw,
                                                                  z, z_rows, z_row0);
   return ls.finish("cft_detect_decode launch");
 }

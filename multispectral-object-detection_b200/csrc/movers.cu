@@ -54,6 +54,7 @@ __device__ __forceinline__ void focus_patch(const T* __restrict__ img, long long
 template <typename T, int kLayout>
 __global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     long long bstride) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const long long npix = static_cast<long long>(B) * Ho * Wo;
   const long long total = kLayout == 0 ? npix : npix * 4;
@@ -86,6 +87,7 @@ __global__ void focus_gather_kernel(const T* __restrict__ img, __nv_bfloat16* __
 // ------------------------------------------------------------------ max pool k x k, stride 1
 __global__ void maxpool_s1_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                                   int B, int H, int W, int C8, int k) {
+  pdl_prologue();
   const long long total = static_cast<long long>(B) * H * W * C8;
   const int r = k / 2;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -130,6 +132,7 @@ __device__ __forceinline__ bf16x8 max8(const bf16x8& a, const bf16x8& b) {
 __global__ void maxpool_cascade_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y0,
                                        __nv_bfloat16* __restrict__ y1, __nv_bfloat16* __restrict__ y2, int ldy, int H,
                                        int W, int k0, int k1, int k2) {
+  pdl_prologue();
   extern __shared__ uint8_t sm_raw[];
   bf16x16* bufA = reinterpret_cast<bf16x16*>(sm_raw);
   bf16x16* bufB = bufA + H * W;
@@ -179,6 +182,7 @@ __global__ void maxpool_cascade_kernel(const __nv_bfloat16* __restrict__ x, int 
 // ------------------------------------------------------------------ nearest 2x upsample
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
                                   int B, int H, int W, int C8) {
+  pdl_prologue();
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = static_cast<long long>(B) * Ho * Wo * C8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -199,6 +203,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int ldx, 
 template <bool kAdd>
 __global__ void addcopy_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
                                int ldb, __nv_bfloat16* __restrict__ y, int ldy, long long npix, int C8) {
+  pdl_prologue();
   const long long total = npix * C8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -220,6 +225,7 @@ __global__ void addcopy_kernel(const __nv_bfloat16* __restrict__ a, int lda, con
 
 // ------------------------------------------------------------------ CUDA-core conv (test cross-check only)
 __global__ void conv_ref_kernel(cft_conv_args a, int Ho, int Wo, int cin_p, int kw) {
+  pdl_prologue();
   const long long total = static_cast<long long>(a.B) * Ho * Wo * a.Cout;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
   const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(a.w);
@@ -273,9 +279,9 @@ extern "C" int cft_focus_gather(const void* img, int in_dtype, int B, int H, int
 #define CFT_FOCUS_LAUNCH(T)                                                                                        \
   do {                                                                                                             \
     if (layout == 0)                                                                                               \
-      focus_gather_kernel<T, 0><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(img), yo, B, H, W, batch_stride); \
+      cft::launch(focus_gather_kernel<T, 0>, dim3(grid), dim3(kThreads), 0, stream, reinterpret_cast<const T*>(img), yo, B, H, W, batch_stride); \
     else                                                                                                           \
-      focus_gather_kernel<T, 1><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(img), yo, B, H, W, batch_stride); \
+      cft::launch(focus_gather_kernel<T, 1>, dim3(grid), dim3(kThreads), 0, stream, reinterpret_cast<const T*>(img), yo, B, H, W, batch_stride); \
   } while (0)
   if (in_dtype == CFT_DT_F32) CFT_FOCUS_LAUNCH(float);
   else if (in_dtype == CFT_DT_BF16) CFT_FOCUS_LAUNCH(__nv_bfloat16);
@@ -302,7 +308,7 @@ extern "C" int cft_maxpool_s1(const void* x, int ldx, int x_coff, void* y, int l
   CFT_REQUIRE(k >= 1 && (k & 1) && B > 0 && H > 0 && W > 0, "cft_maxpool_s1: bad k/shape");
   const long long total = static_cast<long long>(B) * H * W * (C / 8);
   LaunchScope ls(CFT_K_MAXPOOL, stream);
-  maxpool_s1_kernel<<<grid_for(total, kThreads), kThreads, 0, stream>>>(
+  cft::launch(maxpool_s1_kernel, dim3(grid_for(total, kThreads)), dim3(kThreads), 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx, reinterpret_cast<__nv_bfloat16*>(y) + y_coff, ldy, B, H,
       W, C / 8, k);
   return ls.finish("cft_maxpool_s1 launch");
@@ -334,7 +340,7 @@ extern "C" int cft_maxpool_cascade3(const void* x, int ldx, int x_coff, void* y,
   dim3 grid(C / 16, B);
   LaunchScope ls(CFT_K_MAXPOOL, stream);
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
-  maxpool_cascade_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx,
+  cft::launch(maxpool_cascade_kernel, dim3(grid), dim3(threads), smem, stream, reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx,
                                                           yb + y_coff0, yb + y_coff1, yb + y_coff2, ldy, H, W, k0, k1, k2);
   return ls.finish("cft_maxpool_cascade3 launch");
 }
@@ -348,7 +354,7 @@ extern "C" int cft_upsample2x(const void* x, int ldx, int x_coff, void* y, int l
   CFT_REQUIRE(B > 0 && H > 0 && W > 0, "cft_upsample2x: empty shape");
   const long long total = static_cast<long long>(B) * H * W * 4 * (C / 8);
   LaunchScope ls(CFT_K_UPSAMPLE, stream);
-  upsample2x_kernel<<<grid_for(total, kThreads), kThreads, 0, stream>>>(
+  cft::launch(upsample2x_kernel, dim3(grid_for(total, kThreads)), dim3(kThreads), 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx, reinterpret_cast<__nv_bfloat16*>(y) + y_coff, ldy, B, H,
       W, C / 8);
   return ls.finish("cft_upsample2x launch");
@@ -363,7 +369,7 @@ extern "C" int cft_add(const void* a, int lda, int a_coff, const void* b, int ld
   if ((rc = check_slice("cft_add", y, ldy, y_coff, C))) return rc;
   CFT_REQUIRE(npix > 0, "cft_add: empty");
   LaunchScope ls(CFT_K_ADD, stream);
-  addcopy_kernel<true><<<grid_for(npix * (C / 8), kThreads), kThreads, 0, stream>>>(
+  cft::launch(addcopy_kernel<true>, dim3(grid_for(npix * (C / 8), kThreads)), dim3(kThreads), 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(a) + a_coff, lda, reinterpret_cast<const __nv_bfloat16*>(b) + b_coff, ldb,
       reinterpret_cast<__nv_bfloat16*>(y) + y_coff, ldy, npix, C / 8);
   return ls.finish("cft_add launch");
@@ -377,7 +383,7 @@ extern "C" int cft_copy(const void* x, int ldx, int x_coff, void* y, int ldy, in
   if ((rc = check_slice("cft_copy", y, ldy, y_coff, C))) return rc;
   CFT_REQUIRE(npix > 0, "cft_copy: empty");
   LaunchScope ls(CFT_K_COPY, stream);
-  addcopy_kernel<false><<<grid_for(npix * (C / 8), kThreads), kThreads, 0, stream>>>(
+  cft::launch(addcopy_kernel<false>, dim3(grid_for(npix * (C / 8), kThreads)), dim3(kThreads), 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(x) + x_coff, ldx, nullptr, 0,
       reinterpret_cast<__nv_bfloat16*>(y) + y_coff, ldy, npix, C / 8);
   return ls.finish("cft_copy launch");
@@ -392,6 +398,6 @@ extern "C" int cft_conv2d_ref(const cft_conv_args* a, void* stream_v) {
   const long long total = static_cast<long long>(a->B) * Ho * Wo * a->Cout;
   LaunchScope ls(CFT_K_CONV_REF, stream);
   const int kw = a->kw > 0 ? a->kw : a->k;
-  conv_ref_kernel<<<grid_for(total, kThreads, 32), kThreads, 0, stream>>>(*a, Ho, Wo, cin_p, kw);
+  cft::launch(conv_ref_kernel, dim3(grid_for(total, kThreads, 32)), dim3(kThreads), 0, stream, *a, Ho, Wo, cin_p, kw);
   return ls.finish("cft_conv2d_ref launch");
 }

@@ -1,5 +1,6 @@
 // Host-side runtime of libcft_b200: error text, device check, launch counters, profiling.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -41,6 +42,11 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return CFT_OK;
   set_error("%s: %s", what, cudaGetErrorString(e));
   return CFT_E_CUDA;
+}
+
+bool pdl_all() {
+  static const bool on = getenv("CFT_PDL_ALL") != nullptr;
+  return on;
 }
 
 int sm_count() {
