@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFT_ABI_VERSION 3
+#define CFT_ABI_VERSION 4
 
 enum {
   CFT_OK = 0,
@@ -41,7 +41,7 @@ enum {
   CFT_K_CONV_TCGEN05 = 0, CFT_K_CONV_REF = 1, CFT_K_FOCUS = 2, CFT_K_MAXPOOL = 3,
   CFT_K_UPSAMPLE = 4, CFT_K_ADD = 5, CFT_K_COPY = 6, CFT_K_POOL_TOKENS = 7,
   CFT_K_LAYERNORM = 8, CFT_K_ATTENTION = 9, CFT_K_UNPOOL = 10, CFT_K_DETECT = 11,
-  CFT_K_COUNT = 12
+  CFT_K_NMS = 12, CFT_K_COUNT = 13
 };
 
 int cft_abi_version(void);
@@ -163,6 +163,23 @@ int cft_gpt_unpool(const float* tok, int B, int H, int W, int C, int va, int ha,
 int cft_detect_decode(const float* head, int ldh, int B, int ny, int nx, int na, int no,
                       float stride, const float* anchors_px,
                       float* raw, float* z, long long z_rows, long long z_row0, void* stream);
+
+/* Batched non-maximum suppression of Detect's z (the step after the forward: detect_twostream.py:86, test.py:129).
+ * Replaces utils/general.py:455-544 (non_max_suppression), :299-306 (xywh2xyxy) and the torchvision.ops.nms call at
+ * :527 -- results are bit-identical to them (fp32, same operation order, stable descending sort).
+ *   pred   f32 [B, rows, no]: cx, cy, w, h, obj, cls[no-5]   (z of cft_detect_decode)
+ *   keeps obj > conf_thres and conf = cls*obj > conf_thres (best class; every class when multi_label && nc > 1),
+ *   classes/n_classes: optional HOST array of allowed class ids (n_classes = 0: all),
+ *   boxes of different classes never suppress each other unless agnostic (class offset 4096 px, :525),
+ *   at most 30000 candidates per image enter the suppression (:466, :521-522), at most max_det (<= 1024) leave it.
+ *   out    f32 [B, max_det, 6]: x1, y1, x2, y2, conf, cls -- rows [0, counts[b]) valid, descending conf
+ *   counts i32 [B]
+ *   workspace: device scratch of cft_nms_workspace_bytes(B, rows, no - 5, multi_label) bytes, 8-byte aligned.
+ * Not covered: the `labels` (autolabelling) branch (:482-489) and merge-NMS (hard-wired off at :470). */
+long long cft_nms_workspace_bytes(int B, int rows, int nc, int multi_label);
+int cft_nms(const float* pred, int B, int rows, int no, float conf_thres, float iou_thres, int max_det,
+            int multi_label, int agnostic, const int* classes, int n_classes,
+            void* workspace, long long workspace_bytes, float* out, int* counts, void* stream);
 
 /* ---- profiling counters (CUDA events around every launch while enabled) ---- */
 int cft_prof_enable(int on);            /* resets counters when turned on           */

@@ -17,7 +17,7 @@ ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 DT_BF16, DT_F32, DT_U8 = 0, 1, 2
 KERNEL_IDS = {
     "conv_tcgen05": 0, "conv_ref": 1, "focus": 2, "maxpool": 3, "upsample": 4, "add": 5, "copy": 6,
-    "pool_tokens": 7, "layernorm": 8, "attention": 9, "unpool": 10, "detect": 11,
+    "pool_tokens": 7, "layernorm": 8, "attention": 9, "unpool": 10, "detect": 11, "nms": 12,
 }
 
 
@@ -56,6 +56,8 @@ SIGNATURES = {
     "cft_attention": ([_P, _P, _I, _I, _I, _I, _P], _I),
     "cft_gpt_unpool": ([_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P], _I),
     "cft_detect_decode": ([_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _LL, _LL, _P], _I),
+    "cft_nms_workspace_bytes": ([_I, _I, _I, _I], _LL),
+    "cft_nms": ([_P, _I, _I, _I, _F, _F, _I, _I, _I, C.POINTER(_I), _I, _P, _LL, _P, _P, _P], _I),
     "cft_prof_enable": ([_I], _I),
     "cft_prof_get": ([_I, C.POINTER(C.c_double), C.POINTER(_LL)], _I),
     "cft_launch_count": ([], _LL),
