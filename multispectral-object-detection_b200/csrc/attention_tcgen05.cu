@@ -41,8 +41,12 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + tile_bytes;
   uint8_t* sV = sK + tile_bytes;
-  uint8_t* sP = sV + tile_bytes;                     // 2 chunks x [128 x 64] bf16, SWIZZLE_128B (32 KiB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kT * 128);
+  // P: 2 chunks x [128 x 64] bf16, SWIZZLE_128B (32 KiB).  It is written only after S = Q K^T has retired, so for
+  // dk >= 64 it reuses the Q|K tiles (dead by then): 97 KiB per CTA at dk = 128 -> two CTAs per SM, and the 256
+  // (image, head) CTAs of a batch-32 launch run as one wave instead of two.
+  const bool alias_p = 2 * tile_bytes >= 2 * kT * 128;
+  uint8_t* sP = alias_p ? sQ : sV + tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + tile_bytes + (alias_p ? 0 : 2 * kT * 128));
   uint64_t* tma_bar = bars;
   uint64_t* mma_bar = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -214,7 +218,7 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
     set_error("cuTensorMapEncodeTiled(qkv) failed (CUresult %d)", (int)r);
     return CFT_E_CUDA;
   }
-  const int smem = 1024 + 3 * kT * dk * 2 + 2 * kT * 128 + 64;
+  const int smem = 1024 + 3 * kT * dk * 2 + (dk >= 64 ? 0 : 2 * kT * 128) + 64;
   if (!g_attr) {
     int rc = check_cuda(cudaFuncSetAttribute(cft_attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              1024 + 3 * kT * 128 * 2 + 2 * kT * 128 + 64),

@@ -62,6 +62,8 @@ struct ConvParams {
   int b_res_bytes;          // exact bytes of the resident weights (b_res is that, rounded up to 1 KiB)
   int b_res;                // row-reuse mode with the WHOLE weight matrix resident in smem (loaded once per CTA;
                             // the ring then streams activations only): b_res = its size in bytes, 0 = off
+  int teams;                // epilogue teams: 2 = two groups of 8 warps drain alternate tiles (steady state of long tile
+                            // sequences), 1 = all 16 warps share every tile (launches with <= 1 tile per CTA: halves the tail)
   int stage_c;              // bytes per epilogue staging buffer (8 KiB: one bf16 32-column chunk, 16 KiB: two / one f32)
   unsigned long long* span;    // debug (cft_debug_conv_spans): {min CTA start, max CTA end} of this launch in %globaltimer ns
   unsigned long long* trace;   // debug timeline (cft_debug_conv_trace): kTraceSlots clock samples per CTA, else null
@@ -171,7 +173,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     }
     for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], (kEpilogueWarps / kEpiTeams) * kCtas);   // one arrive per warp of the consuming team
+      mbar_init(&tempty_bar[i], (kEpilogueWarps / p.teams) * kCtas);   // one arrive per warp of the consuming team
     }
     for (int i = 0; i < kEpiGroups; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(bres_bar, 1);
@@ -456,8 +458,9 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     // ===================== epilogue: kEpiGroups column groups x 4 warps =====================
     const int ew = warp - 4;
     const int grp = ew >> 2;               // epilogue group 0..3
-    const int team = grp & 1;              // team t drains the accumulators of this CTA's tiles t, t+2, t+4, ...
-    const int cg = grp >> 1;               // column group inside the team: 32-column chunks cg, cg + 2, ...
+    const int teams = p.teams, col_groups = kEpiGroups / teams;
+    const int team = teams == 2 ? (grp & 1) : 0;      // team t drains the accumulators of this CTA's tiles t, t + teams, ...
+    const int cg = teams == 2 ? (grp >> 1) : grp;     // column group inside the team: 32-column chunks cg, cg + col_groups, ...
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;         // accumulator row = pixel within the tile
     const int gtid = (ew & 3) * 32 + lane; // thread index within the group
@@ -466,7 +469,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     float* bias_t = bias_s + team * 256;   // the team's bias copy (teams may be on different n-blocks)
     uint32_t res_phase = 0;
     const int chunks_total = (p.block_n + 31) >> 5;                  // 32-column chunks
-    const int my_chunks = chunks_total > cg ? (chunks_total - cg + kEpiColGroups - 1) / kEpiColGroups : 0;
+    const int my_chunks = chunks_total > cg ? (chunks_total - cg + col_groups - 1) / col_groups : 0;
     const int cps = p.out_f32 ? 1 : (p.stage_c >> 13);               // chunks per staging buffer (8 / 16 KiB)
     const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
     const uint32_t c_chunk_stride = 128u * c_row_bytes;
@@ -475,7 +478,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     int bias_n0 = -1;
     const int bar_id = 1 + grp;
     const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages == 4 ? 2 : 1;
-    for (int j = team;; j += kEpiTeams) {          // j = index in this CTA's tile sequence (the MMA warp walks all j)
+    for (int j = team;; j += teams) {          // j = index in this CTA's tile sequence (the MMA warp walks all j)
       const int tile = work0 + j * work_stride;
       if (tile >= p.num_tiles) break;
       const int acc = j & acc_mask;
@@ -491,13 +494,13 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           if (use_res) {
             mbar_arrive_expect_tx(rbar, static_cast<uint32_t>(nch) * c_box_bytes);
             for (int i = 0; i < nch; ++i)
-              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (cg + kEpiColGroups * (sg + i)) * 32, t.x0,
+              tma_load_4d(stage_c + i * c_chunk_stride, &maps.r, rbar, t.n0 + (cg + col_groups * (sg + i)) * 32, t.x0,
                           t.y0, t.b);
           }
         }
         if (t.n0 != bias_n0) {          // (re)stage this n-block's bias; published by the barrier below
           for (int i = gtid; i < my_chunks * 32; i += 128) {
-            const int col = (cg + kEpiColGroups * (i >> 5)) * 32 + (i & 31);
+            const int col = (cg + col_groups * (i >> 5)) * 32 + (i & 31);
             const int n = t.n0 + col;
             const float bv = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
             bias_t[col] = p.act == 3 ? 0.5f * bv : bv;     // tanh-SiLU consumes h = (acc + bias) / 2 = fma(acc, .5, bias / 2)
@@ -516,7 +519,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
           res_phase ^= 1u;
         }
         for (int ci = 0; ci < nch; ++ci) {
-          const int c0 = (cg + kEpiColGroups * (sg + ci)) * 32;
+          const int c0 = (cg + col_groups * (sg + ci)) * 32;
           uint8_t* stage = stage_c + ci * c_chunk_stride;
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c0), v);
@@ -586,7 +589,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         named_bar_sync(bar_id, 128);
         if (gtid == 0 && !p.dbg_skip_store) {
           for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
-            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (cg + kEpiColGroups * (sg + i)) * 32, t.x0, t.y0, t.b);
+            tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (cg + col_groups * (sg + i)) * 32, t.x0, t.y0, t.b);
           bulk_commit();
         }
       }
@@ -702,6 +705,7 @@ bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
 const bool g_gelu_fast = getenv("CFT_GELU_FAST") != nullptr;   // 2-SFU-op erf-GELU instead of erff
+const bool g_one_team = getenv("CFT_ONE_TEAM") != nullptr;   // experiment: single epilogue team for single-wave launches
 const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
 unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace
 unsigned long long* g_span_buf = nullptr;    // cft_debug_conv_spans
@@ -807,7 +811,14 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.out_f32 = a->out_dtype == CFT_DT_F32;
   // epilogue staging: a 32-column chunk is 128 rows x 64 B (bf16) or x 128 B (f32); column groups that own a single
   // bf16 chunk per tile get 8 KiB buffers, which leaves 32 KiB more for the operand ring
-  const int chunks_per_group = ((p.block_n + 31) / 32 + kEpiColGroups - 1) / kEpiColGroups;
+  // one epilogue team when no CTA gets more than one tile (the small GEMMs of the CFT blocks, the P4/P5 1x1 convs at
+  // small batch): the tail after the last MMA is then one tile drained by 16 warps instead of 8
+  {
+    const int units0 = sm_count() / ctas;
+    p.teams = (g_one_team && p.num_tiles <= units0) ? 1 : kEpiTeams;
+  }
+  const int col_groups_h = kEpiGroups / p.teams;
+  const int chunks_per_group = ((p.block_n + 31) / 32 + col_groups_h - 1) / col_groups_h;
   p.stage_c = (!p.out_f32 && (chunks_per_group <= 1 || g_stage8k)) ? 8 * 1024 : kStageCBytes;
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * p.stage_c;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;

@@ -7,7 +7,10 @@
   (launch-bound at small batch, SURVEY.md §3A) and replayed;
 * two device input/output slots + two copy streams (H2D, D2H): the host->device copy of batch i+1 and the
   device->host copy of detections i-1 overlap the compute of batch i;
-* ``infer(host_u8)`` is the blocking call a user makes; ``submit()/collect()`` expose the pipeline.
+* ``infer(host_u8)`` is the blocking call a user makes; ``submit()/collect()`` expose the pipeline;
+* ``nms={...}`` (arguments of ``nms.nms_batched``) appends the batched NMS kernel to the captured graph, so that the
+  per-step device->host copy is ``[B, max_det, 6]`` detections + counts (0.23 MB at batch 32) instead of the raw
+  ``z [B, 25200, no]`` (25.8 MB) -- the step ``detect_twostream.py:83-86`` performs on the host side of the reference.
 
 The reference has no counterpart (it launches eager PyTorch ops on the default stream, ``test.py:106-119``).
 """
@@ -17,12 +20,15 @@ from typing import List, Optional
 
 import torch
 
+from . import nms as _nms
 from ._lib import CftError, launch_count
 
 
 class ForwardEngine:
-    def __init__(self, model, batch: int, height: int, width: int, device=None, slots: int = 2, use_graph: bool = True):
+    def __init__(self, model, batch: int, height: int, width: int, device=None, slots: int = 2, use_graph: bool = True,
+                 nms: Optional[dict] = None):
         self.model = model.eval()
+        self.nms_kw = dict(nms) if nms is not None else None
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise CftError("ForwardEngine needs a CUDA device (no CPU fallback)")
@@ -39,6 +45,9 @@ class ForwardEngine:
         self.ev_done = [torch.cuda.Event() for _ in range(slots)]
         self.ev_free = [torch.cuda.Event() for _ in range(slots)]
         self.z_host: List[Optional[torch.Tensor]] = [None] * slots
+        self.cnt_dev: List[Optional[torch.Tensor]] = [None] * slots      # with nms: z_dev/z_host hold the detections
+        self.cnt_host: List[Optional[torch.Tensor]] = [None] * slots
+        self._nms_ws: Optional[torch.Tensor] = None
         self.launches_per_forward = 0
         self._next = 0
         self._pending: List[int] = []
@@ -48,7 +57,15 @@ class ForwardEngine:
     def _forward(self, s: int):
         x = self.x_dev[s]
         z, _ = self.model(x[:, :3], x[:, 3:])
-        return z
+        if self.nms_kw is None:
+            return z
+        if self._nms_ws is None:                       # sized once, outside any capture (the warm-up pass comes first)
+            b, rows, no = z.shape
+            ml = bool(self.nms_kw.get("multi_label", False))
+            self._nms_ws = torch.empty((b * rows * (no - 5 if ml else 1),), dtype=torch.int64, device=self.device)
+        det, cnt = _nms.nms_batched(z, workspace=self._nms_ws, **self.nms_kw)
+        self.cnt_dev[s] = cnt
+        return det
 
     def _build(self):
         torch.cuda.synchronize(self.device)
@@ -69,6 +86,8 @@ class ForwardEngine:
                 with torch.cuda.stream(self.compute), torch.no_grad():
                     self.z_dev[s] = self._forward(s)
             self.z_host[s] = torch.empty(self.z_dev[s].shape, dtype=self.z_dev[s].dtype).pin_memory()
+            if self.nms_kw is not None:
+                self.cnt_host[s] = torch.empty(self.cnt_dev[s].shape, dtype=torch.int32).pin_memory()
             self.ev_free[s].record(self.compute)
         self.compute.synchronize()
 
@@ -107,20 +126,26 @@ class ForwardEngine:
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(self.ev_done[s])
             self.z_host[s].copy_(self.z_dev[s], non_blocking=True)
+            if self.nms_kw is not None:
+                self.cnt_host[s].copy_(self.cnt_dev[s], non_blocking=True)
             self.ev_free[s].record(self.d2h)
         self._pending.append(s)
         return s
 
-    def collect(self, slot: Optional[int] = None) -> torch.Tensor:
-        """Wait for the oldest (or the given) submitted batch; returns its detections z on the host (pinned)."""
+    def collect(self, slot: Optional[int] = None):
+        """Wait for the oldest (or the given) submitted batch; returns its detections z on the host (pinned), or with
+        ``nms=...`` the pair (det [B, max_det, 6], counts [B]) -- rows [0, counts[b]) of image b are valid."""
         if not self._pending:
             raise CftError("collect: nothing submitted")
         s = self._pending.pop(0) if slot is None else self._pending.pop(self._pending.index(slot))
         self.ev_free[s].synchronize()
+        if self.nms_kw is not None:
+            return self.z_host[s], self.cnt_host[s]
         return self.z_host[s]
 
-    def infer(self, host_u8: torch.Tensor) -> torch.Tensor:
-        """Blocking convenience call: host uint8 batch in, host fp32 detections ``z [B, rows, no]`` out."""
+    def infer(self, host_u8: torch.Tensor):
+        """Blocking convenience call: host uint8 batch in, host fp32 detections ``z [B, rows, no]`` out
+        (``(det, counts)`` with ``nms=...``)."""
         return self.collect(self.submit(host_u8))
 
     def drain(self):

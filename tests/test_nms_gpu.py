@@ -117,3 +117,25 @@ def test_nms_errors(nms, cft):
         nms.nms_batched(torch.rand(1, 10, 8, device=DEV), max_det=5000)
     out = nms.non_max_suppression(torch.rand(2, 10, 8, device=DEV), classes=[])
     assert all(o.shape == (0, 6) for o in out)
+
+
+def test_forward_engine_with_nms_stage(nms, cft):
+    """ForwardEngine(nms=...) captures forward + NMS in one graph: its (det, counts) equal the oracle NMS of the z the
+    plain engine returns for the same batch (detect_twostream.py:83-86 order of operations)."""
+    from oracle import cft_oracle as O
+    cfg = cft.named_config("yolov5s_fusion_transformerx3_vedai")
+    model = cft.Model(cfg).eval()
+    model.load_state_dict(O.init_state(cfg, seed=13), strict=True)
+    model = model.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.randint(0, 256, (2, 6, 96, 128), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    kw = {"conf_thres": 0.05, "iou_thres": 0.45}
+    plain = cft.ForwardEngine(model, 2, 96, 128, device=DEV)
+    fused = cft.ForwardEngine(model, 2, 96, 128, device=DEV, nms=kw)
+    assert fused.launches_per_forward == plain.launches_per_forward + 1
+    for hb in batches:
+        z = plain.infer(hb).clone()
+        det, counts = fused.infer(hb)
+        ref = N.non_max_suppression(z, **kw)
+        assert sum(r.shape[0] for r in ref) > 0
+        _same([det[i, :int(counts[i])] for i in range(2)], ref, "engine+nms")
