@@ -161,6 +161,91 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def extra_rooflines(pkg, model, B, peaks, dev):
+    """The two kernel classes BASELINE.json's north_star quotes targets for, measured in isolation on this GPU with an
+    L2 flush (256 MiB memset) between timed iterations, median of 5:
+      c3_1x1_hbm   the 1x1 convolutions of the P2/P3 C3 stacks (AI 32-128 flop/B: HBM-bound) -- algorithmic bytes
+                   (input + output + weights, bf16) / time, against the measured HBM peak
+      cft_block_*  one whole CFT block (tokeniser, 8 x [LN, QKV GEMM, attention, out-proj, LN, MLP], ln_f) per scale --
+                   algorithmic FLOPs (24576 d^2 + 524288 d per pair) / time, against the
+                   measured sustained bf16 peak; `attention_core_hbm` is the attention kernel alone, which is HBM-bound
+                   (AI = 64 flop/B): Q, K, V read + O written once per (image, head)."""
+    import math
+    import torch
+    ops = pkg.ops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+    tot_b = tot_ms = 0.0
+    shapes = []
+    for cin, cout, hw, count in ((128, 128, 160, 2), (64, 64, 160, 3), (256, 256, 80, 2), (128, 128, 80, 9)):
+        x = torch.randn(B, cin, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wp, bp = ops.pack_conv_weight(torch.randn(cout, cin, 1, 1) / math.sqrt(cin), torch.zeros(cout), None, device=dev)
+        y = ops.conv2d(x, wp, bp, 1, 1, 1, cout=cout)
+        ms = timed(lambda: ops.conv2d(x, wp, bp, 1, 1, 1, out=y, cout=cout))
+        byts = 2.0 * (B * hw * hw * (cin + cout) + cin * cout)
+        shapes.append({"shape": f"{cin}->{cout} 1x1 @{hw}x{hw}", "us": round(ms * 1e3, 1), "gbs": round(byts / ms / 1e6, 1),
+                       "per_c3_stack_stream": count})
+        tot_b += byts * count
+        tot_ms += ms * count
+        del x, y
+    ach = tot_b / tot_ms / 1e6
+    out["c3_1x1_hbm"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"], "shapes": shapes,
+                         "note": "launch-count-weighted over the 1x1 convs of the P2 (n=3) and P3 (n=9) C3 stacks"}
+    gpts = []
+    for i, m in enumerate(model.model):
+        if not isinstance(m, pkg.GPT):
+            continue
+        d = m.n_embd
+        hw = {256: 80, 512: 40, 1024: 20}.get(d, 40)
+        rgb = torch.randn(B, d, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ir = torch.randn(B, d, hw, hw, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gpts.append((m, rgb, ir))
+        with torch.no_grad():                       # graph replay, like the forward itself (eager launches are host-bound)
+            m.tokens(rgb, ir)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                m.tokens(rgb, ir)
+            ms = timed(gr.replay, n=5)
+        flops = (24576.0 * d * d + 524288.0 * d) * B
+        ach = flops / ms / 1e9
+        out[f"cft_block_d{d}"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                                  "frac": ach / peaks["tflops_sustained"], "ms": round(ms, 4), "layer": i}
+    pkg._lib.prof_enable(True)              # per-launch CUDA events: a separate pass, they would perturb the timing above
+    with torch.no_grad():
+        for m, rgb, ir in gpts:
+            m.tokens(rgb, ir)
+    torch.cuda.synchronize()
+    prof = pkg._lib.prof_get()
+    pkg._lib.prof_enable(False)
+    a_ms, a_n = prof["attention"]
+    if a_n:
+        # 8 attention launches per block and scale; bytes per launch: Q, K, V read + O written = 4 * (B*128) * d * 2 B
+        byts = sum(4.0 * B * 128 * d * 2 for d in (256, 512, 1024)) / 3.0
+        per_launch_ms = a_ms / a_n
+        ach = byts / per_launch_ms / 1e6
+        out["attention_core_hbm"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": ach / peaks["hbm_gbs"], "us_per_launch": round(per_launch_ms * 1e3, 2),
+                                     "note": "mean over the three scales; per-launch CUDA events (includes launch gaps)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +255,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-extras", action="store_true", help="skip the isolated C3-1x1 / CFT-block roofline measurements")
     ap.add_argument("--ncu-range", action="store_true",
                     help="after the measurements, run ONE eager step between cudaProfilerStart/Stop (for ncu "
                          "--profile-from-start off launch lists; numbers printed under ncu are never bench values)")
@@ -317,6 +403,13 @@ def main():
                     "algorithmic_gflop_per_step": conv_flops_step / 1e9,
                     "whole_forward_tensor_frac": (flops_pair * value / world) / (peaks["tflops_sustained"] * 1e12)}
 
+    extras = None
+    if rank == 0 and not args.no_extras:
+        try:
+            extras = extra_rooflines(pkg, model, B, load_peaks(), dev)
+        except Exception as e:          # never lose the headline line over a side measurement
+            extras = {"error": repr(e)[:300]}
+
     if args.ncu_range and rank == 0:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
@@ -339,6 +432,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * K,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms,
+            "rooflines_extra": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -2,7 +2,7 @@
 # Round-1 late session, GPU call 1: full GPU suite (default switches), the suite again with the three new switches on,
 # then A/B step timings of each switch.  Every stage has its own timeout; logs land in gpurun_out/.
 mkdir -p gpurun_out
-run() { name=$1; to=$2; shift 2; echo "=== $name"; /usr/bin/time -f "%es" timeout $to "$@" > gpurun_out/$name.log 2>&1; echo "exit $?" | tee -a gpurun_out/$name.log; tail -n ${TAILN:-12} gpurun_out/$name.log | cut -c1-400; }
+run() { name=$1; to=$2; shift 2; echo "=== $name"; t0=$SECONDS; timeout $to "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($((SECONDS-t0)) s)" | tee -a gpurun_out/$name.log; tail -n ${TAILN:-12} gpurun_out/$name.log | cut -c1-400; }
 TAILN=14 run nms 300 python -m pytest tests/test_nms_gpu.py -q -m gpu --tb=short -x
 TAILN=10 run suite 600 python -m pytest tests -q -m gpu --tb=line --deselect tests/test_nms_gpu.py
 export CFT_PDL_ALL=1 CFT_GELU_FAST=1 CFT_ONE_TEAM=1
