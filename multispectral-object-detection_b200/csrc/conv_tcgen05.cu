@@ -548,7 +548,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
             if (p.act == CFT_ACT_SILU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = silu_fast(f[i]);
-            } else if (p.act == 4) {          // erf-GELU, A&S erf (host: CFT_GELU_FAST)
+            } else if (p.act == 4) {          // erf-GELU, A&S erf (default; CFT_GELU_ERFF=1 selects erff)
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
             } else if (p.act == CFT_ACT_GELU) {
@@ -704,7 +704,7 @@ void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
 bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
-const bool g_gelu_fast = getenv("CFT_GELU_FAST") != nullptr;   // 2-SFU-op erf-GELU instead of erff
+const bool g_gelu_fast = getenv("CFT_GELU_ERFF") == nullptr;   // default: 2-SFU-op erf-GELU; CFT_GELU_ERFF=1 -> erff
 const bool g_one_team = getenv("CFT_ONE_TEAM") != nullptr;   // experiment: single epilogue team for single-wave launches
 const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
 unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace

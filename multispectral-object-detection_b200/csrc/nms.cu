@@ -52,14 +52,6 @@ __device__ __forceinline__ bool iou_gt(const Cand& a, float bx1, float by1, floa
   return ovr > thr;
 }
 
-__device__ __forceinline__ void cmpxchg(unsigned long long* k, int i, int l) {
-  const unsigned long long a = k[i], b = k[l];
-  if (a > b) {
-    k[i] = b;
-    k[l] = a;
-  }
-}
-
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
   pdl_prologue();
   extern __shared__ unsigned long long nms_smem[];
@@ -123,21 +115,49 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
   __syncthreads();
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
-  for (int k = 2; k <= n2; k <<= 1) {
-    const int hk = k >> 1;
-    for (int t = tid; t < (n2 >> 1); t += kNmsThreads) {       // flip step: i <-> block end - offset
-      const int blk = t / hk, off = t - blk * hk;
-      const int i = blk * k + off, l = blk * k + k - 1 - off;
-      if (l < n) cmpxchg(keys, i, l);
+  // pair t of a step: (i, l) with i < l; all strides are powers of two -> shifts and masks only.  Four pairs per thread
+  // are loaded before any is stored (the pairs of one step are disjoint, which the compiler cannot know).
+  const int half = n2 >> 1;
+  auto step = [&](auto pair_of) {
+    for (int t0 = tid; t0 < half; t0 += 4 * kNmsThreads) {
+      int pi[4], pl[4];
+      unsigned long long va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * kNmsThreads;
+        pi[u] = -1;
+        if (t < half) {
+          int i, l;
+          pair_of(t, i, l);
+          if (l < n) {
+            pi[u] = i;
+            pl[u] = l;
+            va[u] = keys[i];
+            vb[u] = keys[l];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (pi[u] >= 0 && va[u] > vb[u]) {
+          keys[pi[u]] = vb[u];
+          keys[pl[u]] = va[u];
+        }
     }
     __syncthreads();
-    for (int j = hk >> 1; j >= 1; j >>= 1) {                   // half cleaners
-      for (int t = tid; t < (n2 >> 1); t += kNmsThreads) {
-        const int i = 2 * j * (t / j) + (t % j), l = i + j;
-        if (l < n) cmpxchg(keys, i, l);
-      }
-      __syncthreads();
-    }
+  };
+  for (int k = 2, lk = 1; k <= n2; k <<= 1, ++lk) {
+    const int hk = k >> 1;
+    step([&](int t, int& i, int& l) {                           // flip step: i <-> block end - offset
+      const int blk = t >> (lk - 1), off = t & (hk - 1);
+      i = (blk << lk) + off;
+      l = (blk << lk) + k - 1 - off;
+    });
+    for (int j = hk >> 1; j >= 1; j >>= 1)                      // half cleaners
+      step([&](int t, int& i, int& l) {
+        i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        l = i + j;
+      });
   }
   if (n > kMaxNms) n = kMaxNms;                                 // utils/general.py:521-522 (top max_nms by confidence)
 

@@ -208,7 +208,7 @@ def detect(xs: List[Tensor], sd, p: str, nc: int, na: int = 3):
         x = x.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()     # :48
         raw.append(x)
         y = x.sigmoid()
-        grid = make_grid(nx, ny)
+        grid = make_grid(nx, ny).to(y.device)
         xy = (y[..., 0:2] * 2.0 - 0.5 + grid) * STRIDES[i]                     # :55
         wh = (y[..., 2:4] * 2) ** 2 * anchor_grid[i]                           # :56
         y = torch.cat((xy, wh, y[..., 4:]), -1)
@@ -223,7 +223,7 @@ def decode_heads(raw: List[Tensor], anchor_grid: Tensor) -> Tensor:
     for i, x in enumerate(raw):
         bs, na, ny, nx, no = x.shape
         y = x.sigmoid()
-        grid = make_grid(nx, ny)
+        grid = make_grid(nx, ny).to(y.device)
         xy = (y[..., 0:2] * 2.0 - 0.5 + grid) * STRIDES[i]
         wh = (y[..., 2:4] * 2) ** 2 * anchor_grid[i]
         y = torch.cat((xy, wh, y[..., 4:]), -1)
