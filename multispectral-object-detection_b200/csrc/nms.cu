@@ -52,7 +52,7 @@ __device__ __forceinline__ bool iou_gt(const Cand& a, float bx1, float by1, floa
   return ovr > thr;
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsArgs a) {
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsArgs a) {
   pdl_prologue();
   extern __shared__ unsigned long long nms_smem[];
   __shared__ int s_n, s_kept, s_first;
