@@ -7,8 +7,10 @@
 //   O = P V        tcgen05.mma  128 x dk x 128   (B = V as loaded: [key][dk] = MN-major operand)
 //   out = O / rowsum  -> bf16, heads merged ([B*128, C])
 //
-// Swizzle mode of the Q/K/V tiles follows the head dim: dk*2 bytes per row -> 32B / 64B / 128B
-// (dk = 128: two 64-wide chunks).  Replaces models/common.py:497-510 (two batched matmuls + softmax that
+// The head dim is cut into chunks of 64 / 32 / 16 elements (widest first: 128 = 64+64, 80 = 64+16, 160 = 64+64+32);
+// every chunk is its own [128 x width] tile with the swizzle mode that matches its row length (128B / 64B / 32B),
+// loaded through the tensor map of that width.  QK^T walks the chunks along K; PV issues one MMA group per chunk
+// (N = chunk width) into that chunk's TMEM columns (a uniform 64-wide split is issued as ONE N = dk group).  Replaces models/common.py:497-510 (two batched matmuls + softmax that
 // materialise the [B,8,128,128] attention tensor in HBM).
 #include "cft_common.cuh"
 #include "tcgen05_ptx.cuh"
@@ -20,24 +22,31 @@ using namespace cft::ptx;
 constexpr int kT = 128;          // tokens
 constexpr int kThreads = 128;
 
+constexpr int kMaxChunks = 4;
 struct AttnParams {
   int C, heads, dk;
-  int bw;          // box width in elements = min(dk, 64)
-  int nchunk;      // dk / bw
-  int layout;      // UMMA layout type of the Q/K/V tiles (2 = SW128, 4 = SW64, 6 = SW32)
+  int nchunk;                 // head-dim chunks
+  int cw[kMaxChunks];         // chunk width in elements (64 / 32 / 16)
+  int coff[kMaxChunks];       // first head-dim element of the chunk
+  int soff[kMaxChunks];       // byte offset of the chunk's [128 x cw] tile inside a Q / K / V tile
+  int layout[kMaxChunks];     // UMMA layout type (2 = SW128, 4 = SW64, 6 = SW32)
+  int map[kMaxChunks];        // tensor map index (0: 64-wide, 1: 32-wide, 2: 16-wide boxes)
+  int uniform64;              // every chunk is 64 wide -> PV as one N = dk MMA group (LBO = chunk stride)
+  int tmem_cols;              // 256 or 512
   float scale_log2e;
   __nv_bfloat16* out;
 };
+struct __align__(64) AttnMaps {
+  CUtensorMap m[3];
+};
 
 __global__ void __launch_bounds__(kThreads)
-cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__ AttnParams p) {
+cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row_bytes = p.bw * 2;
-  const int chunk_bytes = kT * row_bytes;            // one [128 x bw] tile
-  const int tile_bytes = chunk_bytes * p.nchunk;     // one of Q / K / V
+  const int tile_bytes = kT * p.dk * 2;              // one of Q / K / V (all chunks)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + tile_bytes;
   uint8_t* sV = sK + tile_bytes;
@@ -52,12 +61,12 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   if (tid == 0) {
-    prefetch_tmap(&qkv_map);
+    for (int c = 0; c < p.nchunk; ++c) prefetch_tmap(&maps.m[p.map[c]]);
     mbar_init(tma_bar, 1);
     mbar_init(mma_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -72,10 +81,11 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
     mbar_arrive_expect_tx(tma_bar, 3u * static_cast<uint32_t>(tile_bytes));
     const int r0 = b * kT;
     for (int c = 0; c < p.nchunk; ++c) {
-      const int col = h * p.dk + c * p.bw;
-      tma_load_2d(sQ + c * chunk_bytes, &qkv_map, tma_bar, col, r0);
-      tma_load_2d(sK + c * chunk_bytes, &qkv_map, tma_bar, p.C + col, r0);
-      tma_load_2d(sV + c * chunk_bytes, &qkv_map, tma_bar, 2 * p.C + col, r0);
+      const int col = h * p.dk + p.coff[c];
+      const CUtensorMap* m = &maps.m[p.map[c]];
+      tma_load_2d(sQ + p.soff[c], m, tma_bar, col, r0);
+      tma_load_2d(sK + p.soff[c], m, tma_bar, p.C + col, r0);
+      tma_load_2d(sV + p.soff[c], m, tma_bar, 2 * p.C + col, r0);
     }
   }
   mbar_wait(tma_bar, 0);
@@ -84,12 +94,12 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
   // ---- S = Q K^T : K-major operands; 8-row groups are 8*row_bytes apart (SBO) ----
   if (tid == 0) {
     const uint32_t idesc = umma_idesc_ex(128, 128, 0, 0);
-    const uint32_t sbo = 8u * row_bytes;
     int kk = 0;
     for (int c = 0; c < p.nchunk; ++c) {
-      for (int k = 0; k < p.bw / 16; ++k, ++kk) {
-        const uint64_t da = umma_desc(smem_u32(sQ + c * chunk_bytes) + k * 32, 0, sbo, p.layout);
-        const uint64_t db = umma_desc(smem_u32(sK + c * chunk_bytes) + k * 32, 0, sbo, p.layout);
+      const uint32_t sbo = 8u * static_cast<uint32_t>(p.cw[c]) * 2u;      // 8-row groups are 8 * row_bytes apart
+      for (int k = 0; k < p.cw[c] / 16; ++k, ++kk) {
+        const uint64_t da = umma_desc(smem_u32(sQ + p.soff[c]) + k * 32, 0, sbo, p.layout[c]);
+        const uint64_t db = umma_desc(smem_u32(sK + p.soff[c]) + k * 32, 0, sbo, p.layout[c]);
         umma_bf16(tmem_s, da, db, idesc, kk > 0 ? 1u : 0u);
       }
     }
@@ -134,13 +144,20 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
 
   // ---- O = P V : A = P (K-major, SW128, two 64-key chunks), B = V (MN-major as loaded) ----
   if (tid == 0) {
-    const uint32_t idesc = umma_idesc_ex(128, static_cast<uint32_t>(p.dk), 0, 1);
-    const uint32_t sbo_v = 8u * row_bytes;                      // next 8 keys
-    const uint32_t lbo_v = static_cast<uint32_t>(chunk_bytes);  // next 64 head-dim elements (dk = 128 only)
-    for (int k = 0; k < kT / 16; ++k) {
-      const uint64_t da = umma_desc(smem_u32(sP + (k >> 2) * (kT * 128)) + (k & 3) * 32, 0, 1024, 2);
-      const uint64_t db = umma_desc(smem_u32(sV) + k * 16 * row_bytes, lbo_v, sbo_v, p.layout);
-      umma_bf16(tmem_o, da, db, idesc, k > 0 ? 1u : 0u);
+    // one MMA group per head-dim chunk (N = chunk width, its own TMEM columns); a uniform 64-wide split runs as a
+    // single N = dk group whose descriptor steps from chunk to chunk through LBO
+    const int groups = p.uniform64 ? 1 : p.nchunk;
+    for (int c = 0; c < groups; ++c) {
+      const uint32_t n = p.uniform64 ? static_cast<uint32_t>(p.dk) : static_cast<uint32_t>(p.cw[c]);
+      const uint32_t row_b = static_cast<uint32_t>(p.cw[c]) * 2u;
+      const uint32_t idesc = umma_idesc_ex(128, n, 0, 1);
+      const uint32_t sbo_v = 8u * row_b;                        // next 8 keys
+      const uint32_t lbo_v = static_cast<uint32_t>(kT) * row_b; // next chunk of head-dim elements (uniform64 only)
+      for (int k = 0; k < kT / 16; ++k) {
+        const uint64_t da = umma_desc(smem_u32(sP + (k >> 2) * (kT * 128)) + (k & 3) * 32, 0, 1024, 2);
+        const uint64_t db = umma_desc(smem_u32(sV + p.soff[c]) + k * 16 * row_b, lbo_v, sbo_v, p.layout[c]);
+        umma_bf16(tmem_o + static_cast<uint32_t>(p.coff[c]), da, db, idesc, k > 0 ? 1u : 0u);
+      }
     }
     umma_commit(mma_bar);
   }
@@ -165,7 +182,7 @@ cft_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap qkv_map, const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -184,13 +201,28 @@ EncodeTiledFn get_encode() {
 }
 bool g_attr = false;
 
+int launch_attention(const AttnMaps& maps, const AttnParams& p, int B, cudaStream_t stream) {
+  const int dk = p.dk, heads = p.heads;
+  const int smem = 1024 + 3 * kT * dk * 2 + (dk >= 64 ? 0 : 2 * kT * 128) + 64;
+  if (!g_attr) {
+    int rc = check_cuda(cudaFuncSetAttribute(cft_attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             1024 + 3 * kT * 256 * 2 + 64),
+                        "cudaFuncSetAttribute(attention_tcgen05)");
+    if (rc) return rc;
+    g_attr = true;
+  }
+  dim3 grid(heads, B);
+  LaunchScope ls(CFT_K_ATTENTION, stream);
+  cft::launch(cft_attention_tcgen05_kernel, dim3(grid), dim3(kThreads), smem, stream, maps, p);
+  return ls.finish("cft_attention (tcgen05) launch");
+}
 }  // namespace
 
 namespace cft {
 // Returns CFT_E_UNSUPPORTED when the shape is outside this kernel (caller falls back to the CUDA-core kernel).
 int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads, cudaStream_t stream) {
   const int dk = C / heads;
-  if (T != kT || C % heads || !(dk == 16 || dk == 32 || dk == 64 || dk == 128) || B > 65535) return CFT_E_UNSUPPORTED;
+  if (T != kT || C % heads || dk % 16 || dk < 16 || dk > 256 || B > 65535) return CFT_E_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(qkv) % 16 || (3 * C) % 8) return CFT_E_UNSUPPORTED;
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -198,37 +230,51 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
     return CFT_E_CUDA;
   }
   AttnParams p;
+  memset(&p, 0, sizeof(p));
   p.C = C; p.heads = heads; p.dk = dk;
-  p.bw = dk < 64 ? dk : 64;
-  p.nchunk = dk / p.bw;
-  p.layout = p.bw == 64 ? 2 : (p.bw == 32 ? 4 : 6);
-  p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  CUtensorMap map;
-  cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)B * kT};
-  cuuint64_t str[1] = {(cuuint64_t)(3 * C) * 2};
-  cuuint32_t box[2] = {(cuuint32_t)p.bw, (cuuint32_t)kT};
-  cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle swz = p.bw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                            : (p.bw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, str, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(qkv) failed (CUresult %d)", (int)r);
-    return CFT_E_CUDA;
+  {
+    int off = 0, soff = 0, n = 0;
+    bool used[3] = {false, false, false};
+    while (off < dk) {
+      const int rem = dk - off;
+      const int w = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+      if (n == kMaxChunks) return CFT_E_UNSUPPORTED;
+      p.cw[n] = w;
+      p.coff[n] = off;
+      p.soff[n] = soff;
+      p.layout[n] = w == 64 ? 2 : (w == 32 ? 4 : 6);
+      p.map[n] = w == 64 ? 0 : (w == 32 ? 1 : 2);
+      used[p.map[n]] = true;
+      off += w;
+      soff += kT * w * 2;
+      ++n;
+    }
+    p.nchunk = n;
+    p.uniform64 = (dk % 64 == 0) ? 1 : 0;
+    p.tmem_cols = (128 + dk <= 256) ? 256 : 512;
+    p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    AttnMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int i = 0; i < 3; ++i) {
+      if (!used[i]) continue;
+      const int w = i == 0 ? 64 : (i == 1 ? 32 : 16);
+      cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)B * kT};
+      cuuint64_t str[1] = {(cuuint64_t)(3 * C) * 2};
+      cuuint32_t box[2] = {(cuuint32_t)w, (cuuint32_t)kT};
+      cuuint32_t estr[2] = {1, 1};
+      const CUtensorMapSwizzle swz = w == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (w == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      CUresult r = enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, str, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(qkv, box %d) failed (CUresult %d)", w, (int)r);
+        return CFT_E_CUDA;
+      }
+    }
+    return launch_attention(maps, p, B, stream);
   }
-  const int smem = 1024 + 3 * kT * dk * 2 + (dk >= 64 ? 0 : 2 * kT * 128) + 64;
-  if (!g_attr) {
-    int rc = check_cuda(cudaFuncSetAttribute(cft_attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             1024 + 3 * kT * 128 * 2 + 2 * kT * 128 + 64),
-                        "cudaFuncSetAttribute(attention_tcgen05)");
-    if (rc) return rc;
-    g_attr = true;
-  }
-  dim3 grid(heads, B);
-  LaunchScope ls(CFT_K_ATTENTION, stream);
-  cft::launch(cft_attention_tcgen05_kernel, dim3(grid), dim3(kThreads), smem, stream, map, p);
-  return ls.finish("cft_attention (tcgen05) launch");
 }
+
 }  // namespace cft
