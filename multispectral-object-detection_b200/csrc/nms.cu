@@ -5,9 +5,10 @@
 //   2. sort     bitonic network (all-ascending form, so the virtual +inf padding never moves) in shared memory
 //               (<= 26 k candidates; 640x640 has 25200 rows) or in the L2-resident workspace beyond that:
 //               conf descending, candidate id ascending == the stable descending sort of torchvision.ops.nms
-//   3. greedy   1024 candidates per chunk, one per thread: test against the kept list, then resolve the chunk warp by
-//               warp (32x32 IoU bit matrix by shuffles, serial scan replicated on every lane), broadcast the newly kept
-//               boxes through smem; stops at max_det kept boxes (the reference truncates afterwards: same result,
+//   3. greedy   1024 candidates per chunk, one per thread: test against the kept list, then resolve the chunk 32
+//               candidates per round (the 32x32 IoU bit matrix is computed by all 32 warps, one IoU per thread; the
+//               serial scan over its rows is replayed by every warp), the newly kept boxes go through smem to the
+//               threads that still hold live candidates; stops at max_det kept boxes (the reference truncates afterwards: same result,
 //               a greedy decision depends on earlier kept boxes only)
 //
 // Integer/index work is exact; the fp32 arithmetic uses the reference's operation order with explicit round-to-nearest
@@ -48,6 +49,9 @@ __device__ __forceinline__ bool iou_gt(const Cand& a, float bx1, float by1, floa
   const float w = fmaxf(0.f, __fsub_rn(fminf(a.x2, bx2), fmaxf(a.x1, bx1)));
   const float h = fmaxf(0.f, __fsub_rn(fminf(a.y2, by2), fmaxf(a.y1, by1)));
   const float inter = __fmul_rn(w, h);
+  // disjoint boxes (the common case): 0 / x is 0, -0 or NaN, never > thr >= 0 -- skip the IEEE division (its operand
+  // check sends a zero numerator down the slow path)
+  if (inter == 0.f && thr >= 0.f) return false;
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, barea), inter));
   return ovr > thr;
 }
@@ -55,8 +59,9 @@ __device__ __forceinline__ bool iou_gt(const Cand& a, float bx1, float by1, floa
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsArgs a) {
   pdl_prologue();
   extern __shared__ unsigned long long nms_smem[];
-  __shared__ int s_n, s_kept, s_first;
-  __shared__ unsigned s_alive[kNmsWarps];
+  __shared__ int s_n, s_kept;
+  __shared__ unsigned s_alive[kNmsWarps], s_sup[32];
+  __shared__ float s_batch[5][32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* pred = a.pred + static_cast<long long>(b) * a.rows * a.no;
   unsigned long long* ws = a.keys_ws + static_cast<long long>(b) * a.cap;
@@ -206,43 +211,44 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         if (iou_gt(kb, c.x1, c.y1, c.x2, c.y2, c.area, thr)) alive = false;
       }
     }
-    // resolve the chunk: one warp per round (the first warp that still has live candidates)
+    // resolve the chunk: one warp's 32 candidates per round (the first warp that still has live ones).  All 32 warps
+    // take part: warp w computes row w of the batch's 32x32 suppression matrix (one IoU per thread), every warp then
+    // replays the short serial scan over the 32 row masks, so no result has to be broadcast.
     for (;;) {
       const unsigned m = __ballot_sync(0xffffffffu, alive);
       if (lane == 0) s_alive[warp] = m;
       __syncthreads();
       const int kept_before = s_kept;
       if (kept_before >= a.max_det) break;
-      if (tid == 0) {
-        int f = -1;
-        for (int w = 0; w < kNmsWarps; ++w)
-          if (s_alive[w]) {
-            f = w;
-            break;
-          }
-        s_first = f;
+      const unsigned wm = s_alive[lane];                        // lane l looks at warp l (kNmsWarps == 32)
+      const unsigned nz = __ballot_sync(0xffffffffu, wm != 0u);
+      if (nz == 0u) break;
+      const int fw = __ffs(nz) - 1;
+      const unsigned fm = __shfl_sync(0xffffffffu, wm, fw);     // live candidates of the batch
+      if (warp == fw) {
+        s_batch[0][lane] = c.x1; s_batch[1][lane] = c.y1; s_batch[2][lane] = c.x2; s_batch[3][lane] = c.y2;
+        s_batch[4][lane] = c.area;
       }
       __syncthreads();
-      const int fw = s_first;
-      if (fw < 0) break;
+      {
+        const Cand r{s_batch[0][warp], s_batch[1][warp], s_batch[2][warp], s_batch[3][warp], s_batch[4][warp]};
+        const bool sup = lane > warp &&
+                         iou_gt(r, s_batch[0][lane], s_batch[1][lane], s_batch[2][lane], s_batch[3][lane], s_batch[4][lane], thr);
+        const unsigned row = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0) s_sup[warp] = row;
+      }
+      __syncthreads();
+      unsigned remaining = fm, keptmask = 0;
+      int room = a.max_det - kept_before;
+      while (remaining && room > 0) {
+        const int l = __ffs(remaining) - 1;
+        keptmask |= 1u << l;
+        --room;
+        remaining &= ~(1u << l);
+        remaining &= ~s_sup[l];
+      }
+      const int kept_now = kept_before + __popc(keptmask);
       if (warp == fw) {
-        // suppression mask of this lane's candidate over the later lanes of the warp
-        unsigned sup = 0;
-        for (int l = 0; l < 32; ++l) {
-          const float bx1 = __shfl_sync(0xffffffffu, c.x1, l), by1 = __shfl_sync(0xffffffffu, c.y1, l);
-          const float bx2 = __shfl_sync(0xffffffffu, c.x2, l), by2 = __shfl_sync(0xffffffffu, c.y2, l);
-          const float bar = __shfl_sync(0xffffffffu, c.area, l);
-          if (l > lane && iou_gt(c, bx1, by1, bx2, by2, bar, thr)) sup |= 1u << l;
-        }
-        unsigned remaining = m, keptmask = 0;
-        int room = a.max_det - kept_before;
-        while (remaining && room > 0) {
-          const int l = __ffs(remaining) - 1;
-          keptmask |= 1u << l;
-          --room;
-          remaining &= ~(1u << l);
-          remaining &= ~__shfl_sync(0xffffffffu, sup, l);
-        }
         if ((keptmask >> lane) & 1u) {
           const int k = kept_before + __popc(keptmask & ((1u << lane) - 1u));
           kx1[k] = c.x1; ky1[k] = c.y1; kx2[k] = c.x2; ky2[k] = c.y2; kar[k] = c.area;
@@ -250,10 +256,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
           o[0] = ux1; o[1] = uy1; o[2] = ux2; o[3] = uy2; o[4] = conf; o[5] = clsf;
         }
         alive = false;                                          // every candidate of this warp is decided
-        if (lane == 0) s_kept = kept_before + __popc(keptmask);
+        if (lane == 0) s_kept = kept_now;
       }
       __syncthreads();
-      const int kept_now = s_kept;
       if (alive) {
         for (int k = kept_before; k < kept_now && alive; ++k) {
           const Cand kb{kx1[k], ky1[k], kx2[k], ky2[k], kar[k]};

@@ -133,3 +133,17 @@ def test_focus_weight_reindexing_is_a_6x6_stride2_conv(cft):
     assert torch.allclose(w6[:, :18, :6].reshape(16, 3, 6, 6), k66, atol=2e-3, rtol=1e-3)   # fp16 rounding only
     y = F.conv2d(x.double(), k66.double(), b.double(), stride=2, padding=2)
     assert y.shape == ref.shape and torch.allclose(y, ref, atol=1e-12)
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package directory may import or execute it (no CPU fallback,
+    no checker on the product path)."""
+    pkg_dir = os.path.join(ROOT, "multispectral-object-detection_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg_dir):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text or "cft_oracle" in text:
+                    offenders.append(os.path.join(dirpath, fn))
+    assert not offenders, offenders
