@@ -36,7 +36,8 @@ pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb, const __nv
     const int cv = threadIdx.x % nv, sl = threadIdx.x / nv;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (sl < slices) {
-      for (int p = sl; p < npix; p += slices) {
+#pragma unroll 4
+      for (int p = sl; p < npix; p += slices) {       // independent 16-byte loads: keep several in flight
         const int y = y0 + p / bw, x = x0 + p % bw;
         float f[8];
         unpack8(*reinterpret_cast<const bf16x8*>(src + ((static_cast<long long>(b) * H + y) * W + x) * ld + (v0 + cv) * 8), f);
@@ -479,8 +480,12 @@ extern "C" int cft_gpt_unpool(const float* tok, int B, int H, int W, int C, int 
   LaunchScope ls(CFT_K_UNPOOL, stream);
   const int chunks = (C + kUnpoolCC - 1) / kUnpoolCC;
   if (H <= 65535 && chunks <= 65535 && B <= 65535 && ha <= 64) {
-    int threads = W * (kUnpoolCC / 8);
-    threads = threads > 512 ? 512 : (threads < 64 ? 64 : (threads + 31) / 32 * 32);
+    // one (pixel, 8-channel vector) item per thread and pass: balance the passes (640 items = 1 pass of 640 threads, not
+    // 512 + 128) so that no pass runs mostly empty
+    const int items = W * (kUnpoolCC / 8);
+    const int passes = (items + 1023) / 1024;
+    int threads = ((items + passes - 1) / passes + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
     dim3 grid(H, chunks, B);
     cft::launch(unpool_rows_kernel, dim3(grid), dim3(threads), 2 * ha * kUnpoolCC * sizeof(float), stream, a);
   } else {
