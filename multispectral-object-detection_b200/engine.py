@@ -5,8 +5,11 @@
 
 * the whole 47-layer forward (~350 kernel launches) is captured once per buffer slot into a CUDA graph
   (launch-bound at small batch, SURVEY.md §3A) and replayed;
-* two device input/output slots + two copy streams (H2D, D2H): the host->device copy of batch i+1 and the
+* two (or more) device input/output slots + two copy streams (H2D, D2H): the host->device copy of batch i+1 and the
   device->host copy of detections i-1 overlap the compute of batch i;
+* every slot replays its graph on its OWN compute stream, so consecutive batches overlap on the GPU as well: one
+  batch's latency-bound CFT chains (a few dozen CTAs) and kernel tails leave SMs that the next batch's convolutions
+  use (``concurrent=False`` serialises the slots on one stream);
 * ``infer(host_u8)`` is the blocking call a user makes; ``submit()/collect()`` expose the pipeline;
 * ``nms={...}`` (arguments of ``nms.nms_batched``) appends the batched NMS kernel to the captured graph, so that the
   per-step device->host copy is ``[B, max_det, 6]`` detections + counts (0.23 MB at batch 32) instead of the raw
@@ -26,7 +29,7 @@ from ._lib import CftError, launch_count
 
 class ForwardEngine:
     def __init__(self, model, batch: int, height: int, width: int, device=None, slots: int = 2, use_graph: bool = True,
-                 nms: Optional[dict] = None):
+                 nms: Optional[dict] = None, concurrent: bool = True):
         self.model = model.eval()
         self.nms_kw = dict(nms) if nms is not None else None
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
@@ -35,7 +38,10 @@ class ForwardEngine:
         self.shape = (batch, 6, height, width)
         self.slots = slots
         self.use_graph = use_graph
-        self.compute = torch.cuda.Stream(self.device)
+        self.concurrent = bool(concurrent) and slots > 1
+        n_streams = slots if self.concurrent else 1
+        self.computes = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        self.compute = self.computes[0]               # slot s runs on computes[s] (all on computes[0] when not concurrent)
         self.h2d = torch.cuda.Stream(self.device)     # separate copy streams: a D2H queued behind a compute event
         self.d2h = torch.cuda.Stream(self.device)     # must not block the next batch's H2D
         self.x_dev = [torch.zeros(self.shape, dtype=torch.uint8, device=self.device) for _ in range(slots)]
@@ -52,6 +58,9 @@ class ForwardEngine:
         self._next = 0
         self._pending: List[int] = []
         self._build()
+
+    def stream_of(self, slot: int) -> "torch.cuda.Stream":
+        return self.computes[slot] if self.concurrent else self.computes[0]
 
     # ------------------------------------------------------------------ setup
     def _forward(self, s: int):
@@ -77,24 +86,27 @@ class ForwardEngine:
             self.launches_per_forward = launch_count() - n0
         self.compute.synchronize()
         for s in range(self.slots):
+            st = self.stream_of(s)
             if self.use_graph:
                 g = torch.cuda.CUDAGraph()
-                with torch.no_grad(), torch.cuda.graph(g, stream=self.compute):
+                with torch.no_grad(), torch.cuda.graph(g, stream=st):
                     self.z_dev[s] = self._forward(s)
                 self.graphs[s] = g
             else:
-                with torch.cuda.stream(self.compute), torch.no_grad():
+                with torch.cuda.stream(st), torch.no_grad():
                     self.z_dev[s] = self._forward(s)
+                st.synchronize()
             self.z_host[s] = torch.empty(self.z_dev[s].shape, dtype=self.z_dev[s].dtype).pin_memory()
             if self.nms_kw is not None:
                 self.cnt_host[s] = torch.empty(self.cnt_dev[s].shape, dtype=torch.int32).pin_memory()
-            self.ev_free[s].record(self.compute)
-        self.compute.synchronize()
+            self.ev_free[s].record(st)
+        for st in self.computes:
+            st.synchronize()
 
     # ------------------------------------------------------------------ device-resident replay (kernel-only timing)
     def run_resident(self, slot: int = 0):
-        """One forward over whatever is in the slot's device input buffer, on the engine's compute stream."""
-        with torch.cuda.stream(self.compute):
+        """One forward over whatever is in the slot's device input buffer, on the slot's compute stream."""
+        with torch.cuda.stream(self.stream_of(slot)):
             if self.use_graph:
                 self.graphs[slot].replay()
             else:
@@ -115,14 +127,15 @@ class ForwardEngine:
             self.h2d.wait_event(self.ev_free[s])            # slot's previous result has left the device
             self.x_dev[s].copy_(host_u8, non_blocking=True)
             self.ev_in[s].record(self.h2d)
-        with torch.cuda.stream(self.compute):
-            self.compute.wait_event(self.ev_in[s])
+        st = self.stream_of(s)
+        with torch.cuda.stream(st):
+            st.wait_event(self.ev_in[s])
             if self.use_graph:
                 self.graphs[s].replay()
             else:
                 with torch.no_grad():
                     self.z_dev[s] = self._forward(s)
-            self.ev_done[s].record(self.compute)
+            self.ev_done[s].record(st)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(self.ev_done[s])
             self.z_host[s].copy_(self.z_dev[s], non_blocking=True)
@@ -151,6 +164,7 @@ class ForwardEngine:
     def drain(self):
         while self._pending:
             self.collect()
-        self.compute.synchronize()
+        for st in self.computes:
+            st.synchronize()
         self.h2d.synchronize()
         self.d2h.synchronize()
