@@ -53,7 +53,7 @@ class ForwardEngine:
         self.z_host: List[Optional[torch.Tensor]] = [None] * slots
         self.cnt_dev: List[Optional[torch.Tensor]] = [None] * slots      # with nms: z_dev/z_host hold the detections
         self.cnt_host: List[Optional[torch.Tensor]] = [None] * slots
-        self._nms_ws: Optional[torch.Tensor] = None
+        self._nms_ws: Optional[List[torch.Tensor]] = None
         self.launches_per_forward = 0
         self._next = 0
         self._pending: List[int] = []
@@ -68,11 +68,12 @@ class ForwardEngine:
         z, _ = self.model(x[:, :3], x[:, 3:])
         if self.nms_kw is None:
             return z
-        if self._nms_ws is None:                       # sized once, outside any capture (the warm-up pass comes first)
-            b, rows, no = z.shape
+        if self._nms_ws is None:                       # sized once, outside any capture (the warm-up pass comes first);
+            b, rows, no = z.shape                      # one workspace per slot: slots run concurrently
             ml = bool(self.nms_kw.get("multi_label", False))
-            self._nms_ws = torch.empty((b * rows * (no - 5 if ml else 1),), dtype=torch.int64, device=self.device)
-        det, cnt = _nms.nms_batched(z, workspace=self._nms_ws, **self.nms_kw)
+            self._nms_ws = [torch.empty((b * rows * (no - 5 if ml else 1),), dtype=torch.int64, device=self.device)
+                            for _ in range(self.slots)]
+        det, cnt = _nms.nms_batched(z, workspace=self._nms_ws[s], **self.nms_kw)
         self.cnt_dev[s] = cnt
         return det
 
