@@ -255,6 +255,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--slots", type=int, default=4,
+                    help="engine slots = batches in flight (each slot: own graph, own stream; >= 3 keeps two computing "
+                         "while a third copies)")
     ap.add_argument("--no-extras", action="store_true", help="skip the isolated C3-1x1 / CFT-block roofline measurements")
     ap.add_argument("--ncu-range", action="store_true",
                     help="after the measurements, run ONE eager step between cudaProfilerStart/Stop (for ncu "
@@ -318,7 +321,7 @@ def main():
     torch.cuda.synchronize()
 
     # ---------------- the serving executor: CUDA-graph replay + double-buffered copy pipeline ----------------
-    engine = pkg.ForwardEngine(model, B, H, W, device=dev, slots=2, use_graph=not args.no_graph)
+    engine = pkg.ForwardEngine(model, B, H, W, device=dev, slots=args.slots, use_graph=not args.no_graph)
     launches_per_step = engine.launches_per_forward
     for s_ in range(engine.slots):
         engine.x_dev[s_].copy_(x6)
