@@ -255,9 +255,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--slots", type=int, default=4,
-                    help="engine slots = batches in flight (each slot: own graph, own stream; >= 3 keeps two computing "
-                         "while a third copies)")
+    ap.add_argument("--slots", type=int, default=2, help="engine slots (double-buffered copy pipeline)")
+    ap.add_argument("--concurrent", action="store_true",
+                    help="experiment: one compute stream per slot (batches overlap on the GPU); measured: no gain")
     ap.add_argument("--no-extras", action="store_true", help="skip the isolated C3-1x1 / CFT-block roofline measurements")
     ap.add_argument("--ncu-range", action="store_true",
                     help="after the measurements, run ONE eager step between cudaProfilerStart/Stop (for ncu "
@@ -321,7 +321,8 @@ def main():
     torch.cuda.synchronize()
 
     # ---------------- the serving executor: CUDA-graph replay + double-buffered copy pipeline ----------------
-    engine = pkg.ForwardEngine(model, B, H, W, device=dev, slots=args.slots, use_graph=not args.no_graph)
+    engine = pkg.ForwardEngine(model, B, H, W, device=dev, slots=args.slots, use_graph=not args.no_graph,
+                               concurrent=args.concurrent)
     launches_per_step = engine.launches_per_forward
     for s_ in range(engine.slots):
         engine.x_dev[s_].copy_(x6)
@@ -331,8 +332,8 @@ def main():
     torch.cuda.synchronize()
 
     # ---------------- timed region: K steps, device-resident inputs ----------------
-    # Step i replays slot (i mod 2)'s graph on that slot's stream: two batches are in flight, so one batch's latency-bound
-    # CFT chains and kernel tails overlap the other's convolutions (each step is still one full forward of one batch).
+    # Step i replays slot (i mod slots)'s graph; all slots share one compute stream unless --concurrent (an experiment:
+    # batches overlapping on the GPU bought nothing measurable and cost 2-3 % end to end, profiles/r01_timeline.md).
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cur = torch.cuda.current_stream()
     barrier()

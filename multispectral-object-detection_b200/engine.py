@@ -7,9 +7,10 @@
   (launch-bound at small batch, SURVEY.md §3A) and replayed;
 * two (or more) device input/output slots + two copy streams (H2D, D2H): the host->device copy of batch i+1 and the
   device->host copy of detections i-1 overlap the compute of batch i;
-* every slot replays its graph on its OWN compute stream, so consecutive batches overlap on the GPU as well: one
-  batch's latency-bound CFT chains (a few dozen CTAs) and kernel tails leave SMs that the next batch's convolutions
-  use (``concurrent=False`` serialises the slots on one stream);
+* ``concurrent=True`` gives every slot its own compute stream so that consecutive batches overlap on the GPU as well.
+  Measured (profiles/r01_timeline.md, v15): device-resident throughput +0–2 % (run-to-run noise is 1.5 %), end-to-end
+  throughput −2–3 % (the copy pipeline of a slot no longer hides behind exactly one other compute), so the default is
+  one compute stream, slots serialised;
 * ``infer(host_u8)`` is the blocking call a user makes; ``submit()/collect()`` expose the pipeline;
 * ``nms={...}`` (arguments of ``nms.nms_batched``) appends the batched NMS kernel to the captured graph, so that the
   per-step device->host copy is ``[B, max_det, 6]`` detections + counts (0.23 MB at batch 32) instead of the raw
@@ -29,7 +30,7 @@ from ._lib import CftError, launch_count
 
 class ForwardEngine:
     def __init__(self, model, batch: int, height: int, width: int, device=None, slots: int = 2, use_graph: bool = True,
-                 nms: Optional[dict] = None, concurrent: bool = True):
+                 nms: Optional[dict] = None, concurrent: bool = False):
         self.model = model.eval()
         self.nms_kw = dict(nms) if nms is not None else None
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
