@@ -36,3 +36,16 @@ def gather_detections(z_local: torch.Tensor, n_pairs: int) -> List[torch.Tensor]
     outs = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(outs, padded)
     return [o[: hi - lo] for o, (lo, hi) in zip(outs, bounds)]
+
+
+def gather_nms(det_local: torch.Tensor, counts_local: torch.Tensor, n_pairs: int) -> List[torch.Tensor]:
+    """Optional: collect the batched-NMS results of every rank (``nms.nms_batched``: ``det [b, max_det, 6]``,
+    ``counts [b]``) and return one ``[n_i, 6]`` tensor per image pair, in global pair order, on every rank --
+    7.2 KB per pair on the wire instead of the 0.8 MB of its raw ``z``."""
+    dets = gather_detections(det_local, n_pairs)
+    cnts = gather_detections(counts_local.view(-1, 1), n_pairs)
+    out: List[torch.Tensor] = []
+    for d, c in zip(dets, cnts):
+        for i, k in enumerate(c.view(-1).tolist()):
+            out.append(d[i, : int(k)])
+    return out

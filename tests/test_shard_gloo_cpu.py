@@ -29,7 +29,16 @@ def _worker(rank, world, port, n_pairs, q):
     shards = shard.gather_detections(z_local, n_pairs)
     z = torch.cat(shards, 0)
     t = shard.max_over_ranks(10.0 + rank)
-    q.put((rank, lo, hi, z[:, 0, 0].tolist(), t))
+    # batched-NMS results: image g keeps (g % 3) + 1 boxes, every value = g
+    det = torch.zeros(hi - lo, 5, 6)
+    cnt = torch.zeros(hi - lo, dtype=torch.int32)
+    for j, gidx in enumerate(range(lo, hi)):
+        cnt[j] = (gidx % 3) + 1
+        det[j, : int(cnt[j])] = float(gidx)
+    per_image = shard.gather_nms(det, cnt, n_pairs)
+    nms_ok = len(per_image) == n_pairs and all(
+        d.shape == ((g % 3) + 1, 6) and bool((d == float(g)).all()) for g, d in enumerate(per_image))
+    q.put((rank, lo, hi, z[:, 0, 0].tolist(), t, nms_ok))
     dist.destroy_process_group()
 
 
@@ -49,6 +58,7 @@ def test_shard_partition_and_collectives_world2():
     for r in res:
         assert r[3] == [float(i) for i in range(n_pairs)]       # pair order preserved after the gather
         assert r[4] == 11.0                                      # max over ranks
+        assert r[5]                                              # NMS results gathered per image, in pair order
 
 
 def test_shard_bounds_cover_exactly():
