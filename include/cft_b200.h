@@ -191,6 +191,25 @@ int cft_debug_conv_trace(void* buf);
 /* debug: {first CTA start, last CTA end} in %globaltimer ns of each of the next max_launches conv launches */
 int cft_debug_conv_spans(void* buf, int max_launches);
 
+/* The launch plan cft_conv2d would use for `a` (tiling, pipeline depth, shared memory) WITHOUT touching the device:
+ * pointers in `a` are only checked for null / alignment.  Host-side tests walk every conv / linear shape of the
+ * yolov5{s,l,x}-x3 graphs through it (tests/test_conv_plan_cpu.py). */
+typedef struct cft_conv_plan {
+  int ctas;                 /* 1, or 2 = CTA pairs (cta_group::2, UMMA M = 256)                         */
+  int TW, TH;               /* output-pixel tile of one CTA (TW * TH <= 128)                              */
+  int Ho, Wo, tiles_x, tiles_y, m_tiles;
+  int block_n, n_blocks;    /* N tile and their number (n_blocks * block_n >= Cout)                        */
+  int num_tiles;            /* work items (pairs of m-tiles with ctas == 2) x n-blocks                     */
+  int kelems, kchunks, ups; /* K unit (16 / 32 / 64 elements), units per tap, units per ring stage         */
+  int halo;                 /* 3x3 row-reuse mode                                                          */
+  int stages, a_slot, b_slot, b_res;   /* operand ring depth, slot bytes, resident-weight bytes           */
+  int acc_stages, acc_cols; /* TMEM accumulator ring (acc_stages * acc_cols == 512)                        */
+  int teams, stage_c;       /* epilogue teams, bytes per epilogue staging buffer                           */
+  int smem_bytes;           /* dynamic shared memory of the launch                                          */
+  int grid;                 /* CTAs launched                                                               */
+} cft_conv_plan;
+int cft_debug_conv_plan(const cft_conv_args* a, cft_conv_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,14 @@ class ConvArgs(C.Structure):
     ]
 
 
+class ConvPlan(C.Structure):
+    """struct cft_conv_plan (include/cft_b200.h): the launch plan cft_conv2d would use, computed on the host."""
+    _fields_ = [(n, C.c_int) for n in (
+        "ctas", "TW", "TH", "Ho", "Wo", "tiles_x", "tiles_y", "m_tiles", "block_n", "n_blocks", "num_tiles",
+        "kelems", "kchunks", "ups", "halo", "stages", "a_slot", "b_slot", "b_res", "acc_stages", "acc_cols",
+        "teams", "stage_c", "smem_bytes", "grid")]
+
+
 _I, _P, _LL, _F = C.c_int, C.c_void_p, C.c_longlong, C.c_float
 # name -> argtypes; every symbol include/cft_b200.h declares (tests check the export list).
 SIGNATURES = {
@@ -44,6 +52,7 @@ SIGNATURES = {
     "cft_conv2d_ref": ([C.POINTER(ConvArgs), _P], _I),
     "cft_debug_conv_trace": ([_P], _I),
     "cft_debug_conv_spans": ([_P, _I], _I),
+    "cft_debug_conv_plan": ([C.POINTER(ConvArgs), C.POINTER(ConvPlan)], _I),
     "cft_focus_gather": ([_P, _I, _I, _I, _I, _LL, _I, _P, _P], _I),
     "cft_focus_conv": ([_P, _I, _I, _I, _LL, _P, _P, _I, _I, _P, _I, _I, _P], _I),
     "cft_maxpool_s1": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),

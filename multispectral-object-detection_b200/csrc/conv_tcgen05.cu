@@ -710,6 +710,7 @@ const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumula
 unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace
 unsigned long long* g_span_buf = nullptr;    // cft_debug_conv_spans
 int g_span_next = 0, g_span_max = 0;
+thread_local cft_conv_plan* g_plan_out = nullptr;   // cft_debug_conv_plan: report the plan instead of launching
 const bool g_no_bres = getenv("CFT_NO_BRES") != nullptr;     // debug: never keep the weights resident
 const bool g_stage8k = getenv("CFT_STAGE8K") != nullptr;     // experiment: 8 KiB staging buffers for every bf16 output
 const bool g_no_pdl = getenv("CFT_NO_PDL") != nullptr;
@@ -848,6 +849,20 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.y = a->y;
   p.res = a->res;
 
+  if (g_plan_out != nullptr) {      // planning only (host tests): nothing below is device-independent
+    cft_conv_plan* o = g_plan_out;
+    o->ctas = ctas; o->TW = p.TW; o->TH = p.TH; o->Ho = p.Ho; o->Wo = p.Wo;
+    o->tiles_x = p.tiles_x; o->tiles_y = p.tiles_y; o->m_tiles = p.m_tiles;
+    o->block_n = p.block_n; o->n_blocks = p.n_blocks; o->num_tiles = p.num_tiles;
+    o->kelems = p.kelems; o->kchunks = p.kchunks; o->ups = p.ups; o->halo = p.halo;
+    o->stages = p.stages; o->a_slot = p.a_slot; o->b_slot = p.b_slot; o->b_res = p.b_res;
+    o->acc_stages = p.acc_stages; o->acc_cols = p.acc_cols; o->teams = p.teams; o->stage_c = p.stage_c;
+    o->smem_bytes = 1024 + p.stages * stage_bytes + p.b_res + kEpiGroups * p.stage_c + kTailBytes;
+    int units_p = sm_count() / ctas;
+    if (units_p > p.num_tiles) units_p = p.num_tiles;
+    o->grid = units_p * ctas;
+    return CFT_OK;
+  }
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a->x) + a->x_coff;
@@ -968,4 +983,13 @@ extern "C" int cft_debug_conv_spans(void* buf, int max_launches) {
   g_span_next = 0;
   g_span_max = buf ? max_launches : 0;
   return CFT_OK;
+}
+
+extern "C" int cft_debug_conv_plan(const cft_conv_args* a, cft_conv_plan* plan) {
+  CFT_REQUIRE(plan != nullptr, "cft_debug_conv_plan: null plan");
+  memset(plan, 0, sizeof(*plan));
+  g_plan_out = plan;
+  const int rc = cft_conv2d(a, nullptr);
+  g_plan_out = nullptr;
+  return rc;
 }
