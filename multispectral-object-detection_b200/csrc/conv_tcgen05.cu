@@ -849,7 +849,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.y = a->y;
   p.res = a->res;
 
-  if (g_plan_out != nullptr) {      // planning only (host tests): nothing below is device-independent
+  if (g_plan_out != nullptr) {      // planning only (host tests): everything below needs the driver / a device
     cft_conv_plan* o = g_plan_out;
     o->ctas = ctas; o->TW = p.TW; o->TH = p.TH; o->Ho = p.Ho; o->Wo = p.Wo;
     o->tiles_x = p.tiles_x; o->tiles_y = p.tiles_y; o->m_tiles = p.m_tiles;

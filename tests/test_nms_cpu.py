@@ -69,3 +69,101 @@ def test_nms_wrapper_fails_loudly_without_cuda(cft):
     nms = import_module("multispectral-object-detection_b200.nms")
     with pytest.raises(cft.CftError):
         nms.non_max_suppression(torch.rand(1, 10, 8))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The two algorithmic claims csrc/nms.cu rests on, emulated step by step in Python (the kernel itself is covered by
+# tests/test_nms_gpu.py): (1) the all-ascending bitonic network with VIRTUAL +inf padding sorts any n, (2) resolving
+# the sorted candidates in chunks, one 32-candidate batch per round (kept-list test -> 32x32 suppression matrix ->
+# serial scan over its rows -> broadcast of the newly kept boxes), is the sequential greedy suppression.
+# ---------------------------------------------------------------------------------------------------------------------
+def _bitonic_virtual_padding(keys):
+    import numpy as np
+    k_ = np.array(keys, dtype=np.uint64)
+    n = len(k_)
+    n2 = 1
+    while n2 < n:
+        n2 <<= 1
+
+    def step(pair_of):
+        for t in range(n2 >> 1):
+            i, l = pair_of(t)
+            if l < n and k_[i] > k_[l]:                     # pairs whose upper index is padding are skipped
+                k_[i], k_[l] = k_[l], k_[i]
+    k, lk = 2, 1
+    while k <= n2:
+        hk = k >> 1
+        step(lambda t: (((t >> (lk - 1)) << lk) + (t & (hk - 1)), ((t >> (lk - 1)) << lk) + k - 1 - (t & (hk - 1))))
+        j = hk >> 1
+        while j >= 1:
+            step(lambda t, j=j: (((t & ~(j - 1)) << 1) | (t & (j - 1)), (((t & ~(j - 1)) << 1) | (t & (j - 1))) + j))
+            j >>= 1
+        k <<= 1
+        lk += 1
+    return k_
+
+
+def test_kernel_sort_network_with_virtual_padding():
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 3, 5, 17, 100, 257, 1000, 1025, 1500):
+        a = rng.integers(0, 40, size=n).astype(np.uint64)       # many ties
+        assert (_bitonic_virtual_padding(a) == np.sort(a)).all(), n
+
+
+def _chunked_greedy(boxes, scores, thr, max_det, chunk=64, warp=8):
+    """csrc/nms.cu phase 3 with `chunk` threads of `warp` lanes (the kernel: 1024 / 32)."""
+    import numpy as np
+    f = np.float32
+    thr = f(thr)
+
+    def gt(a, b):                                              # iou_gt(a = earlier box, b = later box)
+        w = max(f(0), f(min(a[2], b[2]) - max(a[0], b[0])))
+        h = max(f(0), f(min(a[3], b[3]) - max(a[1], b[1])))
+        inter = f(w * h)
+        if inter == 0 and thr >= 0:
+            return False
+        with np.errstate(all="ignore"):
+            return f(inter / f(f(a[4] + b[4]) - inter)) > thr
+    n = len(scores)
+    order = np.argsort(-scores, kind="stable")
+    area = ((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])).astype(f)
+    cand = [(boxes[i, 0], boxes[i, 1], boxes[i, 2], boxes[i, 3], area[i]) for i in order]
+    kept, kept_idx = [], []
+    for base in range(0, n, chunk):
+        if len(kept) >= max_det:
+            break
+        m = min(chunk, n - base)
+        alive = [t < m and not any(gt(kb, cand[base + t]) for kb in kept) for t in range(chunk)]
+        while True:
+            kept_before = len(kept)
+            if kept_before >= max_det:
+                break
+            warps_alive = [any(alive[w * warp:(w + 1) * warp]) for w in range(chunk // warp)]
+            if not any(warps_alive):
+                break
+            fw = warps_alive.index(True)
+            lanes = list(range(fw * warp, (fw + 1) * warp))
+            sup = {l: {l2 for l2 in lanes if l2 > l and l2 < m and l < m and gt(cand[base + l], cand[base + l2])} for l in lanes}
+            remaining = [l for l in lanes if alive[l]]
+            room = max_det - kept_before
+            while remaining and room > 0:
+                l = remaining.pop(0)
+                kept.append(cand[base + l])
+                kept_idx.append(int(order[base + l]))
+                room -= 1
+                remaining = [x for x in remaining if x not in sup[l]]
+            for l in lanes:
+                alive[l] = False
+            for t in range(m):
+                if alive[t] and any(gt(kb, cand[base + t]) for kb in kept[kept_before:]):
+                    alive[t] = False
+    return kept_idx
+
+
+@pytest.mark.parametrize("seed,max_det", [(0, 300), (1, 20), (2, 300), (3, 7)])
+def test_kernel_round_structure_equals_sequential_greedy(seed, max_det):
+    p = N.make_predictions(1, 600, 3, seed)[0].numpy()
+    box, sc = N.xywh2xyxy(p[:, :4]), p[:, 4]
+    ref = N.nms_greedy(box, sc, 0.45, limit=max_det).tolist()
+    assert _chunked_greedy(box, sc, 0.45, max_det) == ref
