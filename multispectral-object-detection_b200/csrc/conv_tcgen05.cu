@@ -8,11 +8,14 @@
 //    (py, px), W/H strides doubled) so every tap is again a dense box.
 //    1x1 convs and nn.Linear are the same kernel with taps = 1, H = B = 1, W = M.
 //  * W tiles come from a 3-D map (Cin, taps, Cout) over the packed [Cout][taps][Cin_p] weights.
-//  * 128B-swizzled K-major smem tiles feed tcgen05.mma (UMMA 128 x block_n x 16, bf16 -> fp32),
-//    accumulators live in TMEM (2 x 256 columns, double buffered across tiles).
-//  * Warp roles (256 threads, persistent CTAs, static round-robin tile schedule):
-//      warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM alloc | warps 4-7 epilogue
-//    Epilogue: tcgen05.ld -> +bias -> SiLU/GELU -> +residual -> bf16/f32 -> global (NHWC slice).
+//  * 128B / 64B / 32B-swizzled K-major smem tiles feed tcgen05.mma (UMMA 128 x block_n x 16, or 256 x block_n x 16 for a
+//    CTA pair with cta_group::2; bf16 -> fp32); accumulators live in TMEM as a ring of 4 x 128 or 2 x 256 columns.
+//  * Warp roles (640 threads, persistent CTAs, static round-robin tile schedule):
+//      warp 0 TMA producer | warp 1 MMA issuer (one elected lane) | warp 2 TMEM alloc | warps 4-19 epilogue
+//    Epilogue (2 teams x 2 column groups x 4 warps): tcgen05.ld -> +bias -> SiLU / GELU -> +residual (TMA-loaded tile)
+//    -> bf16 / f32 -> swizzled smem staging -> TMA store into the NHWC channel slice.
+//  * 3x3 stride-1 'row-reuse' mode: one (TH + 2) x TW pixel box per filter column serves the three vertical taps;
+//    small weight matrices stay resident in smem; 1x1 convs walk a flat [B*H*W, C] matrix.  DESIGN.md section 3.1.
 //
 // Replaces the cuDNN/cuBLAS calls the reference reaches through nn.Conv2d / nn.Linear
 // (models/common.py:41-50,450-453,533-536; models/yolo_test.py:46).
