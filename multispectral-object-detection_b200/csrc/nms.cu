@@ -22,6 +22,7 @@ using namespace cft;
 
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
+static_assert(kNmsWarps == 32, "the round loop maps warp w to lane w of every warp (s_alive[lane], matrix row = warp)");
 constexpr int kMaxDetCap = 1024;
 constexpr int kMaxNms = 30000;             // utils/general.py:466
 constexpr float kMaxWh = 4096.f;           // utils/general.py:464

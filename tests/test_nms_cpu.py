@@ -167,3 +167,25 @@ def test_kernel_round_structure_equals_sequential_greedy(seed, max_det):
     box, sc = N.xywh2xyxy(p[:, :4]), p[:, 4]
     ref = N.nms_greedy(box, sc, 0.45, limit=max_det).tolist()
     assert _chunked_greedy(box, sc, 0.45, max_det) == ref
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_nms_greedy_equals_installed_torchvision(seed):
+    """``nms_greedy`` (the restated CPU algorithm) against the installed ``torchvision.ops.nms`` itself, on random boxes,
+    thresholds and heavy score ties -- kept indices identical and in the same order."""
+    import numpy as np
+    import torchvision
+    g = torch.Generator().manual_seed(1000 + seed)
+    n = int(torch.randint(1, 1500, (1,), generator=g))
+    xy = torch.rand(n, 2, generator=g) * 200
+    wh = torch.rand(n, 2, generator=g) * 80 + 1
+    boxes = torch.cat([xy, xy + wh], 1)
+    scores = torch.rand(n, generator=g)
+    if seed % 3 == 0:
+        scores = (scores * 8).floor() / 8                       # only 8 distinct scores: the stable order decides
+    if seed % 4 == 1:
+        boxes[n // 2:] = boxes[: n - n // 2]                    # exact duplicates
+    thr = float(torch.rand(1, generator=g)) * 0.9
+    ref = torchvision.ops.nms(boxes, scores, thr).numpy()
+    mine = N.nms_greedy(boxes.numpy(), scores.numpy(), thr)
+    assert mine.shape == ref.shape and (mine == ref).all()
