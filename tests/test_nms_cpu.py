@@ -184,7 +184,7 @@ def test_nms_greedy_equals_installed_torchvision(seed):
     if seed % 3 == 0:
         scores = (scores * 8).floor() / 8                       # only 8 distinct scores: the stable order decides
     if seed % 4 == 1:
-        boxes[n // 2:] = boxes[: n - n // 2]                    # exact duplicates
+        boxes[n // 2:] = boxes[: n - n // 2].clone()            # exact duplicates
     thr = float(torch.rand(1, generator=g)) * 0.9
     ref = torchvision.ops.nms(boxes, scores, thr).numpy()
     mine = N.nms_greedy(boxes.numpy(), scores.numpy(), thr)
