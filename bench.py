@@ -110,6 +110,24 @@ def host_threads():
     return max(1, min(n, 64))
 
 
+def fused_state(sd, eps):
+    """Model.fuse() (models/yolo_test.py:296-304, utils/torch_utils.py:181-201) applied to a state dict: the reference's
+    inference entry points run the fused model (attempt_load -> fuse, models/experimental.py:113-134)."""
+    import torch
+    out = {}
+    for k, v in sd.items():
+        if ".bn." in k:
+            continue
+        if k.endswith("conv.weight") and k.replace("conv.weight", "bn.weight") in sd:
+            p = k[:-len("conv.weight")]
+            scale = sd[p + "bn.weight"] / torch.sqrt(sd[p + "bn.running_var"] + eps)
+            out[k] = v * scale.view(-1, 1, 1, 1)
+            out[p + "conv.bias"] = sd[p + "bn.bias"] - sd[p + "bn.running_mean"] * scale
+        else:
+            out[k] = v
+    return out
+
+
 def best_thread_count(fwd, candidates=None):
     """The reference arm may use every host thread, but PyTorch's CPU kernels do not always scale to all of them
     (a batch-1 forward on 64 threads can be slower than on 16): time one forward per candidate thread count and keep the
@@ -136,7 +154,7 @@ def cpu_baseline(seconds_budget=20.0, batch=1):
     from oracle import cft_oracle as O
     pkg = importlib.import_module("multispectral-object-detection_b200")
     cfg = pkg.named_config(CFG_NAME)
-    sd = O.init_state(cfg, seed=0)
+    sd = fused_state(O.init_state(cfg, seed=0), O.BN_EPS)       # BN folded, as the reference's inference path runs
     x, x2 = O.make_inputs(batch, H, W, seed=1)
     best_thread_count(lambda: O.forward(sd, cfg, x, x2))      # also the warm-up
     times, t_start = [], time.perf_counter()
@@ -157,7 +175,7 @@ def run_reference(args, rank):
     from oracle import cft_oracle as O
     pkg = importlib.import_module("multispectral-object-detection_b200")
     cfg = pkg.named_config(CFG_NAME)
-    sd = O.init_state(cfg, seed=0)
+    sd = fused_state(O.init_state(cfg, seed=0), O.BN_EPS)       # BN folded, as the reference's inference path runs
     b = 1                                             # bounded sample per step
     x, x2 = O.make_inputs(b, H, W, seed=1)
     best_thread_count(lambda: O.forward(sd, cfg, x, x2))      # fastest of 8/16/32/all host threads; doubles as warm-up
