@@ -285,6 +285,40 @@ def extra_rooflines(pkg, model, B, peaks, dev):
     return out
 
 
+def gpu_eager_baseline(pkg, cfg, B, dev, steps=5):
+    """The existing GPU path on the same device: the reference's op sequence as PyTorch eager ops (cuDNN / cuBLAS through
+    torch.nn.functional -- the oracle's restatement with its tensors on the GPU), BN fused, bf16, channels_last: what
+    `test.py --half` / `detect_twostream.py` run.  A reported baseline beside cpu_baseline; never on the product path."""
+    import torch
+    from oracle import cft_oracle as O
+    sd = {}
+    for k, v in fused_state(O.init_state(cfg, seed=0), O.BN_EPS).items():
+        if v.is_floating_point():
+            v = v.to(dev, torch.bfloat16)
+            if v.dim() == 4:
+                v = v.contiguous(memory_format=torch.channels_last)
+        else:
+            v = v.to(dev)
+        sd[k] = v
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, H, W, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x2 = torch.rand(B, 3, H, W, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    for _ in range(2):
+        O.forward(sd, cfg, x, x2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        O.forward(sd, cfg, x, x2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del sd, x, x2
+    torch.cuda.empty_cache()
+    return {"value": B / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "kind": "pytorch eager (cuDNN/cuBLAS), BN fused, "
+            "bf16 channels_last, same GPU", "sample": f"{steps} forwards of batch {B} @ {H}x{W}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,6 +331,8 @@ def main():
     ap.add_argument("--slots", type=int, default=2, help="engine slots (double-buffered copy pipeline)")
     ap.add_argument("--concurrent", action="store_true",
                     help="experiment: one compute stream per slot (batches overlap on the GPU); measured: no gain")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the PyTorch-eager (cuDNN/cuBLAS) forward of the same graph on this GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the isolated C3-1x1 / CFT-block roofline measurements")
     ap.add_argument("--ncu-range", action="store_true",
                     help="after the measurements, run ONE eager step between cudaProfilerStart/Stop (for ncu "
@@ -462,6 +498,13 @@ def main():
         except Exception as e:          # never lose the headline line over a side measurement
             extras = {"error": repr(e)[:300]}
 
+    eager = None
+    if rank == 0 and not args.no_eager_baseline:
+        try:
+            eager = gpu_eager_baseline(pkg, cfg, B, dev)
+        except Exception as e:          # a side measurement must never cost the headline line
+            eager = {"error": repr(e)[:300]}
+
     if args.ncu_range and rank == 0:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
@@ -485,7 +528,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * K,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms,
-            "rooflines_extra": extras,
+            "rooflines_extra": extras, "gpu_eager_baseline": eager,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
