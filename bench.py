@@ -499,7 +499,7 @@ def main():
             extras = {"error": repr(e)[:300]}
 
     eager = None
-    if rank == 0 and not args.no_eager_baseline:
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
         try:
             eager = gpu_eager_baseline(pkg, cfg, B, dev)
         except Exception as e:          # a side measurement must never cost the headline line
@@ -515,7 +515,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_baseline()
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()      # rank 0 at N = 1 only
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
