@@ -9,7 +9,8 @@ The directory name carries a hyphen (it mirrors the reference repository's name)
 ``importlib.import_module("multispectral-object-detection_b200")`` or through the root alias
 module ``cft_b200``.
 """
-from . import _lib, allreduce, config, nms, ops, shard  # noqa: F401
+from . import _lib, allreduce, checkpoint, config, nms, ops, shard  # noqa: F401
+from .checkpoint import attempt_load, from_reference_model  # noqa: F401
 from ._lib import CftError, build, load  # noqa: F401
 from .config import named_config, x3_config  # noqa: F401
 from .engine import ForwardEngine  # noqa: F401
@@ -20,4 +21,4 @@ from .modules import (C3, SPP, Add, Add2, Bottleneck, Concat, Conv, Detect, Focu
 
 __all__ = ["Model", "ForwardEngine", "install", "uninstall", "convert", "parse_model", "x3_config", "named_config",
            "Conv", "Focus", "Bottleneck", "C3", "SPP", "Concat", "Add", "Add2", "GPT", "Detect", "Upsample",
-           "build", "load", "CftError", "ops", "config", "nms", "non_max_suppression", "nms_batched", "shard", "allreduce"]
+           "build", "load", "CftError", "ops", "config", "nms", "non_max_suppression", "nms_batched", "shard", "allreduce", "checkpoint", "attempt_load", "from_reference_model"]
