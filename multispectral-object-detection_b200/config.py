@@ -3,7 +3,7 @@
 The reference stores these graphs as yaml files under ``models/transformer/`` and
 feeds them to ``parse_model`` (reference ``models/yolo_test.py:479-555``).  The yaml
 files do not exist on the GPU box, so the same dictionaries are generated here;
-``tests/test_config_host.py`` checks (when ``/root/reference`` is present) that
+``tests/test_host_cpu.py`` checks (when ``/root/reference`` is present) that
 ``x3_config(...)`` equals ``yaml.safe_load`` of every reference x3 yaml.
 
 Row format is the reference's: ``[from, number, module-name, args]``.
