@@ -282,6 +282,20 @@ def extra_rooflines(pkg, model, B, peaks, dev):
         out["attention_core_hbm"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                      "frac": ach / peaks["hbm_gbs"], "us_per_launch": round(per_launch_ms * 1e3, 2),
                                      "note": "mean over the three scales; per-launch CUDA events (includes launch gaps)"}
+    try:        # the step after the forward: batched NMS of a batch-B z (synthetic boxes, reference defaults 0.25 / 0.45)
+        g = torch.Generator().manual_seed(3)
+        pr = torch.rand(B, 25200, 8, generator=g)
+        pr[..., :2] *= float(H)
+        pr[..., 2:4] = 20.0 + 100.0 * pr[..., 2:4]
+        pr = pr.to(dev)
+        det = torch.zeros(B, 300, 6, device=dev)
+        cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = torch.empty(B * 25200, dtype=torch.int64, device=dev)
+        ms = timed(lambda: pkg.nms_batched(pr, out=det, counts=cnt, workspace=ws))
+        out["nms_batch"] = {"us": round(ms * 1e3, 1), "rows_per_image": 25200, "kept_mean": float(cnt.float().mean()),
+                            "note": "cft_nms, one launch for the batch; uniform random boxes"}
+    except Exception as e:
+        out["nms_batch"] = {"error": repr(e)[:200]}
     return out
 
 
