@@ -421,7 +421,7 @@ def convert(ref_model: nn.Module) -> nn.Module:
 def _convert_module(m: nn.Module) -> nn.Module:
     name = type(m).__name__
     if name == "Upsample":
-        return M.Upsample(m.size, m.scale_factor, m.mode)
+        return M.Upsample(m.size, m.scale_factor, m.mode).train(m.training)
     if name not in REGISTRY:
         raise CftError(f"convert: module {name} is outside the CFTx3 hot path")
     if name == "Conv":
@@ -461,4 +461,5 @@ def _convert_module(m: nn.Module) -> nn.Module:
         new.stride = m.stride
     if name in ("Conv", "GPT", "Detect"):
         new.load_state_dict(m.state_dict(), strict=True)
+    new.train(m.training)                       # fresh modules start in training mode: keep the source's mode (eval checkpoints)
     return new

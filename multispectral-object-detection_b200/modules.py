@@ -49,6 +49,15 @@ class _Packed:
         return self.value
 
 
+def _require_eval_bn(bn):
+    """The kernels fold BatchNorm's RUNNING statistics into the conv weights (eval semantics).  A BatchNorm in training
+    mode would need batch statistics (models/common.py:42 under train.py): not built -- fail loudly instead of silently
+    computing the eval result."""
+    if bn is not None and bn.training:
+        raise CftError("BatchNorm in training mode (batch statistics) is not implemented on the B200 forward path: "
+                       "call model.eval() -- the kernels fold the running statistics (utils/torch_utils.py:181-201)")
+
+
 class Conv(nn.Module):
     """reference models/common.py:36-50: SiLU(BN(conv2d(x))) -- one fused tcgen05 kernel launch."""
 
@@ -75,6 +84,7 @@ class Conv(nn.Module):
     def folded(self, device):
         """(packed bf16 weight, fp32 bias) with BN folded (utils/torch_utils.py:181-201)."""
         bn = getattr(self, "bn", None)
+        _require_eval_bn(bn)
         srcs = [self.conv.weight, self.conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
 
         def build():
@@ -113,6 +123,7 @@ class Focus(nn.Module):
         cv = self.conv
         k, s, act = cv._check()
         bn = getattr(cv, "bn", None)
+        _require_eval_bn(bn)
         srcs = [cv.conv.weight, cv.conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
         wide = bool(self.wide) and k == 3 and s == 1
 

@@ -147,3 +147,17 @@ def test_product_package_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text or "cft_oracle" in text:
                     offenders.append(os.path.join(dirpath, fn))
     assert not offenders, offenders
+
+
+def test_training_mode_batchnorm_fails_loudly(cft):
+    """The forward folds BN running statistics (eval semantics); a train-mode BatchNorm must raise, not silently run eval."""
+    conv = cft.Conv(16, 24, 3, 1)
+    assert conv.training
+    with pytest.raises(cft.CftError, match="training mode"):
+        conv.folded("cpu")
+    conv.eval()
+    w, b = conv.folded("cpu")
+    assert w.shape == (24, 9, 16)
+    c3 = cft.C3(16, 16, 1)
+    with pytest.raises(cft.CftError, match="training mode"):
+        c3._cv12("cpu")
