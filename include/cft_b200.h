@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFT_ABI_VERSION 4
+#define CFT_ABI_VERSION 5
 
 enum {
   CFT_OK = 0,
@@ -41,7 +41,7 @@ enum {
   CFT_K_CONV_TCGEN05 = 0, CFT_K_CONV_REF = 1, CFT_K_FOCUS = 2, CFT_K_MAXPOOL = 3,
   CFT_K_UPSAMPLE = 4, CFT_K_ADD = 5, CFT_K_COPY = 6, CFT_K_POOL_TOKENS = 7,
   CFT_K_LAYERNORM = 8, CFT_K_ATTENTION = 9, CFT_K_UNPOOL = 10, CFT_K_DETECT = 11,
-  CFT_K_NMS = 12, CFT_K_COUNT = 13
+  CFT_K_NMS = 12, CFT_K_GPT_BLOCK = 13, CFT_K_COUNT = 14
 };
 
 int cft_abi_version(void);
@@ -142,6 +142,37 @@ int cft_layernorm(const float* x, const float* gamma, const float* beta, float e
  * q|k|v (head h at columns h*dk of each third), T tokens per image (T <= 128),
  * out bf16 [B*T, C] = softmax(q k^T / sqrt(dk)) v with heads merged. */
 int cft_attention(const void* qkv, void* out, int B, int T, int C, int heads, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The transformer stack of one CFT / GPT block in ONE launch (models/common.py:622 `self.trans_blocks(x)` + :625
+ * `self.ln_f(x)`; per layer myTransformerBlock.forward :540-546 with SelfAttention.forward :475-513):
+ *     x += out_proj(softmax(q k^T / sqrt(dk)) v),  q|k|v = Linear(LN1(x));    x += W2 GELU(W1 LN2(x) + b1) + b2
+ * One thread-block cluster per image keeps the 128 x d token tile on chip / in L2 for all layers (csrc/cft_block.cu).
+ *   x_in   f32 [B, 128, d]   tokens (output of cft_gpt_pool_tokens)         x_out  f32 [B, 128, d] = ln_f(x)
+ *   wqkv   bf16 [layers*3d, d]  rows of layer l: que_proj | key_proj | val_proj weights (nn.Linear [out, in])
+ *   wo     bf16 [layers*d, d]   w1 bf16 [layers*4d, d]   w2 bf16 [layers*d, 4d];  biases f32, same row order
+ *   ln1_*, ln2_*  f32 [layers*d] (ln_input / ln_output of every layer),  lnf_*  f32 [d]
+ *   workspace: cft_gpt_block_workspace_bytes(B, d) bytes, 128-byte aligned (all-gathered bf16 operands)
+ *   cluster: CTAs per image (0 = automatic);  debug_x: optional f32 [layers, B, 128, d] dump of x after each layer
+ * Supported: 128 tokens, head dim 16/32/64/128, d <= 512 with d / cluster in {64, 128}
+ * (cft_gpt_block_supported() tells); anything else returns CFT_E_UNSUPPORTED and the caller runs the per-op path
+ * (cft_layernorm / cft_conv2d / cft_attention).
+ * ------------------------------------------------------------------------------------- */
+typedef struct cft_gpt_block_args {
+  int B, tokens, d, heads, layers, cluster;
+  const void* wqkv; const float* bqkv;
+  const void* wo;   const float* bo;
+  const void* w1;   const float* b1;
+  const void* w2;   const float* b2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *lnf_g, *lnf_b;
+  float eps1, eps2, epsf;
+  const float* x_in; float* x_out;
+  void* workspace; long long workspace_bytes;
+  float* debug_x;
+} cft_gpt_block_args;
+long long cft_gpt_block_workspace_bytes(int B, int d);
+int cft_gpt_block_supported(int B, int d, int heads, int tokens);
+int cft_gpt_block(const cft_gpt_block_args* a, void* stream);
 
 /* GPT back end (models/common.py:626-637) fused with Add2 (:239-242) and Add (:229):
  * tok f32 [B, 2*va*ha, C] (after ln_f) is bilinearly upsampled (align_corners=False) to HxW

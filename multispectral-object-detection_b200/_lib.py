@@ -17,7 +17,7 @@ ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 DT_BF16, DT_F32, DT_U8 = 0, 1, 2
 KERNEL_IDS = {
     "conv_tcgen05": 0, "conv_ref": 1, "focus": 2, "maxpool": 3, "upsample": 4, "add": 5, "copy": 6,
-    "pool_tokens": 7, "layernorm": 8, "attention": 9, "unpool": 10, "detect": 11, "nms": 12,
+    "pool_tokens": 7, "layernorm": 8, "attention": 9, "unpool": 10, "detect": 11, "nms": 12, "gpt_block": 13,
 }
 
 
@@ -42,6 +42,22 @@ class ConvPlan(C.Structure):
         "teams", "stage_c", "smem_bytes", "grid")]
 
 
+class GptBlockArgs(C.Structure):
+    """struct cft_gpt_block_args (include/cft_b200.h)."""
+    _fields_ = [
+        ("B", C.c_int), ("tokens", C.c_int), ("d", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
+        ("cluster", C.c_int),
+        ("wqkv", C.c_void_p), ("bqkv", C.c_void_p), ("wo", C.c_void_p), ("bo", C.c_void_p),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p), ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+        ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p),
+        ("eps1", C.c_float), ("eps2", C.c_float), ("epsf", C.c_float),
+        ("x_in", C.c_void_p), ("x_out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+        ("debug_x", C.c_void_p),
+    ]
+
+
 _I, _P, _LL, _F = C.c_int, C.c_void_p, C.c_longlong, C.c_float
 # name -> argtypes; every symbol include/cft_b200.h declares (tests check the export list).
 SIGNATURES = {
@@ -63,6 +79,9 @@ SIGNATURES = {
     "cft_gpt_pool_tokens": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "cft_layernorm": ([_P, _P, _P, _F, _LL, _I, _P, _I, _P], _I),
     "cft_attention": ([_P, _P, _I, _I, _I, _I, _P], _I),
+    "cft_gpt_block_workspace_bytes": ([_I, _I], _LL),
+    "cft_gpt_block_supported": ([_I, _I, _I, _I], _I),
+    "cft_gpt_block": ([C.POINTER(GptBlockArgs), _P], _I),
     "cft_gpt_unpool": ([_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P], _I),
     "cft_detect_decode": ([_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _LL, _LL, _P], _I),
     "cft_nms_workspace_bytes": ([_I, _I, _I, _I], _LL),

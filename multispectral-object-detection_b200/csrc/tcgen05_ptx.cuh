@@ -237,5 +237,27 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
+
+// ------------------------------------------------------------------ thread-block-cluster helpers (cft_block.cu)
+// Split cluster barrier: arrive (release) is non-blocking, wait (acquire) blocks until every thread of the cluster has
+// arrived.  A thread must alternate arrive / wait.  .aligned: executed by all lanes of a converged warp.
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v2f32(uint32_t caddr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(caddr), "f"(a), "f"(b) : "memory");
+}
+// generic-proxy writes (global AND shared) -> visible to the async proxy (TMA) after the following release
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 }  // namespace ptx
 }  // namespace cft

@@ -387,6 +387,9 @@ class GPT(nn.Module):
             module.bias.data.zero_()
             module.weight.data.fill_(1.0)
 
+    # one-launch transformer stack (csrc/cft_block.cu); CFT_NO_FUSED_BLOCK=1 / fused_block = False -> 7 launches per layer
+    fused_block = os.environ.get("CFT_NO_FUSED_BLOCK") is None
+
     def _weights(self, device):
         srcs = [p for p in self.parameters()]
 
@@ -405,18 +408,39 @@ class GPT(nn.Module):
                     "up": ops.pack_linear_weight(blk.mlp[0].weight, blk.mlp[0].bias, device=device),
                     "down": ops.pack_linear_weight(blk.mlp[2].weight, blk.mlp[2].bias, device=device),
                 })
-            return {"layers": layers, "pos": f32(self.pos_emb),
+            # the same parameters stacked over the layers: one tensor per kind for the one-launch kernel (cft_gpt_block)
+            cat = lambda ts: torch.cat(list(ts), 0).contiguous()
+            stack = {
+                "layers": len(layers),
+                "wqkv": cat(L["qkv"][0].view(L["qkv"][0].shape[0], -1) for L in layers), "bqkv": cat(L["qkv"][1] for L in layers),
+                "wo": cat(L["out"][0].view(L["out"][0].shape[0], -1) for L in layers), "bo": cat(L["out"][1] for L in layers),
+                "w1": cat(L["up"][0].view(L["up"][0].shape[0], -1) for L in layers), "b1": cat(L["up"][1] for L in layers),
+                "w2": cat(L["down"][0].view(L["down"][0].shape[0], -1) for L in layers), "b2": cat(L["down"][1] for L in layers),
+                "ln1_g": cat(L["ln1"][0] for L in layers), "ln1_b": cat(L["ln1"][1] for L in layers),
+                "ln2_g": cat(L["ln2"][0] for L in layers), "ln2_b": cat(L["ln2"][1] for L in layers),
+                "lnf_g": f32(self.ln_f.weight), "lnf_b": f32(self.ln_f.bias),
+                "eps1": float(layers[0]["ln1"][2]), "eps2": float(layers[0]["ln2"][2]), "epsf": float(self.ln_f.eps),
+                "uniform_eps": all(L["ln1"][2] == layers[0]["ln1"][2] and L["ln2"][2] == layers[0]["ln2"][2] for L in layers),
+            } if layers else None
+            return {"layers": layers, "pos": f32(self.pos_emb), "stack": stack,
                     "lnf": (f32(self.ln_f.weight), f32(self.ln_f.bias), self.ln_f.eps)}
         return self._packed.get((_versions(*srcs), str(device)), build)
 
     def tokens(self, rgb, ir):
         """Everything up to and including ln_f: fp32 [B, 2*va*ha, d]."""
+        if self.training and any(m.p > 0 for m in self.modules() if isinstance(m, nn.Dropout)):
+            raise CftError("GPT in training mode: the embd / attn / resid dropouts (models/common.py:466-467,537,575) are not "
+                           "implemented on the B200 forward path -- call model.eval()")
         rgb, ir = ops.to_nhwc_bf16(rgb), ops.to_nhwc_bf16(ir)
         assert rgb.shape == ir.shape
         b, c, _, _ = rgb.shape
         t = 2 * self.vert_anchors * self.horz_anchors
         wts = self._weights(rgb.device)
         x = ops.gpt_pool_tokens(rgb, ir, wts["pos"], self.vert_anchors, self.horz_anchors)   # fp32 [B,T,d]
+        st = wts["stack"]
+        if self.fused_block and st is not None and st["uniform_eps"] and ops.gpt_block_supported(b, c, self.h, t):
+            # all layers + ln_f in ONE launch: a cluster of CTAs per image keeps the token tile on chip (csrc/cft_block.cu)
+            return ops.gpt_block(x, st, self.h)
         x2d = x.view(b * t, c)
         for L in wts["layers"]:
             y = ops.layernorm(x2d, *L["ln1"])                                    # bf16 [B*T, d]

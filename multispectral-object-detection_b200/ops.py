@@ -14,12 +14,12 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, DT_BF16, DT_F32, ConvArgs
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, DT_BF16, DT_F32, ConvArgs, GptBlockArgs
 
 __all__ = [
     "ACT_NONE", "ACT_SILU", "ACT_GELU", "empty_nhwc", "to_nhwc_bf16", "conv2d", "gemm", "focus_gather",
     "maxpool_s1", "maxpool_cascade3", "upsample2x", "add", "copy_into", "gpt_pool_tokens", "layernorm", "attention",
-    "gpt_unpool", "detect_decode", "pack_conv_weight", "pack_linear_weight",
+    "gpt_block", "gpt_block_supported", "gpt_unpool", "detect_decode", "pack_conv_weight", "pack_linear_weight",
 ]
 
 
@@ -320,6 +320,38 @@ def attention(qkv: torch.Tensor, b: int, t: int, c: int, heads: int) -> torch.Te
     lib = _lib.lib()
     out = torch.empty((b * t, c), dtype=torch.bfloat16, device=qkv.device)
     _lib.check(lib.cft_attention(qkv.data_ptr(), out.data_ptr(), b, t, c, heads, _stream()), "cft_attention")
+    return out
+
+
+def gpt_block_supported(b: int, d: int, heads: int, tokens: int) -> bool:
+    """True when the fused transformer-stack kernel (``cft_gpt_block``) covers this shape."""
+    return bool(_lib.lib().cft_gpt_block_supported(b, d, heads, tokens))
+
+
+def gpt_block(tok: torch.Tensor, w: dict, heads: int, cluster: int = 0, debug_x: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ln_f(trans_blocks(tok)) in ONE launch (models/common.py:622,625).  ``tok`` fp32 [B,128,d]; ``w``: the stacked
+    per-layer parameters built by ``modules.GPT._weights`` (key ``"stack"``)."""
+    lib = _lib.lib()
+    _require_cuda(tok, "gpt_block tokens")
+    b, t, d = tok.shape
+    if tok.dtype != torch.float32 or not tok.is_contiguous():
+        raise _lib.CftError("gpt_block: tokens must be contiguous fp32 [B,128,d]")
+    if out is None:
+        out = torch.empty_like(tok)
+    need = int(lib.cft_gpt_block_workspace_bytes(b, d))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=tok.device)
+    a = GptBlockArgs()
+    a.B, a.tokens, a.d, a.heads, a.layers, a.cluster = b, t, d, heads, w["layers"], cluster
+    for k in ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "lnf_g", "lnf_b"):
+        setattr(a, k, w[k].data_ptr())
+    a.eps1, a.eps2, a.epsf = w["eps1"], w["eps2"], w["epsf"]
+    a.x_in, a.x_out = tok.data_ptr(), out.data_ptr()
+    a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    a.debug_x = debug_x.data_ptr() if debug_x is not None else None
+    _lib.check(lib.cft_gpt_block(C.byref(a), _stream()), "cft_gpt_block")
+    out._cft_ws = workspace          # the launch is asynchronous: keep the scratch alive with its result
     return out
 
 
