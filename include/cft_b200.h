@@ -173,6 +173,8 @@ typedef struct cft_gpt_block_args {
 long long cft_gpt_block_workspace_bytes(int B, int d);
 int cft_gpt_block_supported(int B, int d, int heads, int tokens);
 int cft_gpt_block(const cft_gpt_block_args* a, void* stream);
+/* debug: per-CTA, per-layer clock samples of the compute warps (16 u64 slots each); NULL = off */
+int cft_debug_block_trace(void* buf);
 
 /* GPT back end (models/common.py:626-637) fused with Add2 (:239-242) and Add (:229):
  * tok f32 [B, 2*va*ha, C] (after ln_f) is bilinearly upsampled (align_corners=False) to HxW

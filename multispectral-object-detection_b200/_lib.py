@@ -82,6 +82,7 @@ SIGNATURES = {
     "cft_gpt_block_workspace_bytes": ([_I, _I], _LL),
     "cft_gpt_block_supported": ([_I, _I, _I, _I], _I),
     "cft_gpt_block": ([C.POINTER(GptBlockArgs), _P], _I),
+    "cft_debug_block_trace": ([_P], _I),
     "cft_gpt_unpool": ([_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P], _I),
     "cft_detect_decode": ([_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _LL, _LL, _P], _I),
     "cft_nms_workspace_bytes": ([_I, _I, _I, _I], _LL),

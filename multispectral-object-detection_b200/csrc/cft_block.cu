@@ -8,20 +8,24 @@
 // [c*DC, (c+1)*DC) of the residual stream (fp32, in REGISTERS for the whole kernel), the heads that live in those
 // columns, and the matching N-slices of all four Linear layers:
 //
-//   QKV   A = LN1(x) [128, d] resident in smem; B = this CTA's q|k|v weight rows streamed by TMA; the accumulator is
-//         drained (+bias, bf16) straight into UMMA-layout Q / K / V smem tiles -> attention never leaves the SM
-//   attn  S = Q K^T (tcgen05), softmax by 256 threads out of TMEM, P -> smem, O = P V (tcgen05), O / rowsum -> L2
-//   out   A = O (all heads, all-gathered through L2) resident; N = DC; epilogue: x += acc + bias, LN2 statistics
-//         exchanged between the CTAs through distributed shared memory, LN2(x) slice -> L2
-//   up    A = LN2(x) resident; N = 4 DC in passes of 256; epilogue: +bias, erf-GELU, bf16 hidden slice -> L2
-//   down  A = hidden [128, 4d] streamed through the operand slots; N = DC; epilogue: x += acc + bias, next LN1 / ln_f
+//   LN    row statistics: per-CTA partial sums exchanged through distributed shared memory (one cluster barrier); every
+//         CTA normalises its own column slice, writes it (bf16, UMMA K-major SWIZZLE_128B layout) into chunk c of its
+//         resident A operand and pushes that 16 KiB chunk into the same place of every peer with a DSMEM bulk copy that
+//         signals the peer's chunk mbarrier -- the all-gather never touches L2 and needs no second barrier
+//   QKV   A = LN1(x) [128, d] resident; B = this CTA's q|k|v weight rows streamed by TMA; the accumulator is drained
+//         (+bias, bf16) straight into UMMA-layout Q / K / V smem tiles -> attention never leaves the SM
+//   attn  two local heads at a time (8 compute warps each): S = Q K^T (tcgen05), softmax out of TMEM, P -> smem,
+//         O = P V (tcgen05), O / rowsum -> registers -> chunk c of the A operand, all-gathered like the LN output
+//   out   A = O resident; N = DC; epilogue: x += acc + bias, then LN2
+//   up    A = LN2(x) resident; N = 4 DC in passes; epilogue: +bias, erf-GELU, bf16 hidden slice -> L2
+//   down  A = hidden [128, 4d] streamed by TMA through the operand slots; N = DC; epilogue: x += acc + bias, next LN1 / ln_f
 //
-// Warp roles (384 threads): warp 0 weight (B) producer | warp 1 MMA issuer | warp 2 activation (A) producer + TMEM
-// allocator | warp 3 idle (keeps the cluster-barrier count) | warps 4-11 compute: thread (t, hh) owns token row
-// t = TMEM lane t and half hh of every column range.
-// Six cluster barriers per layer publish the all-gathered operands (O, LN2(x), hidden, LN1(x)) and the LayerNorm
-// partial sums; the weight producer and the MMA issuer use the split arrive / wait form so that weights of the next
-// GEMM are prefetched across a barrier.
+// Warp roles (640 threads): warp 0 weight (B) producer | warp 1 MMA issuer | warp 2 streamed-A producer + TMEM
+// allocator | warp 3 idle (keeps the cluster-barrier count) | warps 4-19 compute: thread (t, qd) owns token row
+// t = TMEM lane t and quarter qd of every column range.
+// Four cluster barriers per layer: LN1 statistics, attention finished (operand slots free), LN2 statistics, hidden
+// published.  The weight producer and the MMA issuer use the split arrive / wait form, so weights of the next GEMM are
+// prefetched across a barrier.
 //
 // Replaces 56 dependent launches per block (7 per layer: LN, QKV GEMM, attention, out-proj, LN, MLP up, MLP down).
 #include <stdlib.h>
@@ -34,39 +38,52 @@ using namespace cft;
 using namespace cft::ptx;
 
 constexpr int kT = 128;                    // tokens per image (2 * 8 * 8)
-constexpr int kComputeWarps = 8;
-constexpr int kThreads = 128 + 32 * kComputeWarps;   // 384
-constexpr int kStageBytes = 16384;         // weight ring stage: <= 256 rows x 32 k (64 B rows, SWIZZLE_64B)
+constexpr int kComputeWarps = 16;
+constexpr int kCompute = 32 * kComputeWarps;
+constexpr int kThreads = 128 + kCompute;   // 640
 constexpr int kAChunk = 16384;             // activation chunk: 128 rows x 64 k (128 B rows, SWIZZLE_128B)
 constexpr int kMaxStages = 8;
-constexpr int kMaxASlots = 8;
+constexpr int kMaxASlots = 10;
+constexpr int kMaxPasses = 12;
 constexpr int kTmemCols = 512;
-constexpr uint32_t kTmemS = 384;           // S = Q K^T accumulator columns [384, 512)
 constexpr int kSmemMax = 227 * 1024;
+constexpr int kMiscFixed = 512 + 2048 + 2048 + 4096;   // barriers | softmax max | softmax sum | LN quarter partials
 
 struct __align__(64) BlockMaps {
-  CUtensorMap wqkv, wo, w1, w2;   // weights, box {32 k, rows}
-  CUtensorMap abuf, hbuf;         // activations, box {64 k, 128 rows}
+  CUtensorMap w[4];               // wqkv, wo, w1, w2: box {64 k, rows}
+  CUtensorMap hbuf;               // hidden, box {64 k, 128 rows}
+};
+
+// one GEMM pass = one accumulator: N weight rows (1-3 row segments) x all of K
+struct Pass {
+  int map, nseg, seg_rows;
+  int row[3];                     // first weight row of each segment (layer 0, cluster rank 0)
+  int cta_stride, layer_stride;   // row offset per cluster rank / per layer
+  int n, kchunks, kpack;          // MMA N; K / 64; 64-wide K sub-tiles per ring stage
+  int tcol;                       // accumulator TMEM column
+  int a_mode;                     // 0: resident A, wait for its chunks | 1: resident, already waited | 2: streamed
 };
 
 struct BlockParams {
   int B, d, heads, dk, layers, C, hpc;
-  int stages, a_slots, ra_bytes;
+  int stages, stage_bytes, a_slots, ra_bytes;
+  int npass_qkv, npass_up, npass_max;   // passes[0..nq) QKV, [nq] out, [nq+1 .. nq+1+nu) up, [nq+1+nu] down
+  Pass passes[kMaxPasses];
   int cw, nch, layout, rowB;      // attention tiles: chunk width (elements), chunks per head, UMMA layout code, row bytes
+  int p_off;                      // byte offset of the P tiles inside the operand region (dk < 64), -1: P aliases Q|K
   float scale_log2e, eps1, eps2, epsf;
   const float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *lnfg, *lnfb;
   const float* x_in;
   float* x_out;
-  __nv_bfloat16* abuf;            // [3][B*128][d]: LN1(x) | O | LN2(x)
   __nv_bfloat16* hbuf;            // [B*128][4d]
   float* dbg;                     // optional [layers][B][128][d] dump of x after every layer
+  unsigned long long* trace;      // debug (cft_debug_block_trace): [grid][layers][16] clock64 samples of compute warp 0
 };
 
 struct Ring {
   int stage;
   uint32_t phase;
 };
-
 __device__ __forceinline__ void ring_advance(Ring& r, int stages) {
   if (++r.stage == stages) {
     r.stage = 0;
@@ -74,98 +91,43 @@ __device__ __forceinline__ void ring_advance(Ring& r, int stages) {
   }
 }
 
-// ------------------------------------------------------------------ weight producer: one GEMM pass
-__device__ __forceinline__ void produce_pass(const CUtensorMap* map, int nseg, int row0, int row1, int row2, int seg_rows,
-                                             int k32, uint8_t* ring, uint64_t* bfull, uint64_t* bempty, int stages,
-                                             Ring& r) {
-  const uint32_t tx = static_cast<uint32_t>(nseg * seg_rows) * 64u;
-  for (int i = 0; i < k32; ++i) {
-    mbar_wait(&bempty[r.stage], r.phase ^ 1u);
-    if (elect_one_sync()) {
-      uint8_t* dst = ring + r.stage * kStageBytes;
-      mbar_arrive_expect_tx(&bfull[r.stage], tx);
-      tma_load_2d(dst, map, &bfull[r.stage], i * 32, row0);
-      if (nseg > 1) tma_load_2d(dst + seg_rows * 64, map, &bfull[r.stage], i * 32, row1);
-      if (nseg > 2) tma_load_2d(dst + 2 * seg_rows * 64, map, &bfull[r.stage], i * 32, row2);
-    }
-    __syncwarp();
-    ring_advance(r, stages);
-  }
-}
-
-// ------------------------------------------------------------------ MMA issuer: one GEMM pass
-// a_mode 0: A resident, chunk barriers not yet consumed | 1: A resident, already waited for | 2: A streamed (slot ring)
-__device__ __forceinline__ void mma_pass(uint32_t ra_addr, uint32_t ring_addr, int a_mode, int n, int k32,
-                                         uint32_t d_tmem, uint64_t* afull, uint64_t* aempty, int a_slots,
-                                         uint32_t& a_par, uint64_t* bfull, uint64_t* bempty, int stages, Ring& r,
-                                         uint64_t* acc_bar) {
-  const uint32_t idesc = umma_idesc_ex(128u, static_cast<uint32_t>(n), 0, 0);
-  constexpr uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, SWIZZLE_128B
-  constexpr uint32_t b_hi = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO 512 B, SWIZZLE_64B
-  for (int i = 0; i < k32; ++i) {
-    const int chunk = i >> 1;
-    const int slot = a_mode == 2 ? chunk % a_slots : chunk;
-    if ((i & 1) == 0 && a_mode != 1) {
-      mbar_wait(&afull[slot], (a_par >> slot) & 1u);
-      a_par ^= 1u << slot;
-    }
-    mbar_wait(&bfull[r.stage], r.phase);
-    tc_fence_after();
-    if (elect_one_sync()) {
-      const uint32_t a_lo = (ra_addr + static_cast<uint32_t>(slot) * kAChunk + static_cast<uint32_t>(i & 1) * 64u) >> 4;
-      const uint32_t b_lo = (ring_addr + static_cast<uint32_t>(r.stage) * kStageBytes) >> 4;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {            // two K = 16 steps per 32-element stage (+32 B inside the swizzle atom)
-        const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | ((a_lo + 2u * s) & 0x3FFFu);
-        const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | ((b_lo + 2u * s) & 0x3FFFu);
-        umma_bf16(d_tmem, da, db, idesc, (i | s) != 0 ? 1u : 0u);
-      }
-      umma_commit(&bempty[r.stage]);
-      if (a_mode == 2 && (i & 1)) umma_commit(&aempty[slot]);
-      if (i == k32 - 1) umma_commit(acc_bar);
-    }
-    __syncwarp();
-    ring_advance(r, stages);
-  }
-}
-
 // ------------------------------------------------------------------ the kernel
-template <int DC>
+template <int DC, int HP>      // columns per CTA; head PAIRS per CTA
 __global__ void __launch_bounds__(kThreads, 1)
 cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_constant__ BlockParams p) {
-  constexpr int NC = DC / 2;                       // residual-stream columns per compute thread
-  constexpr int NQP = (3 * DC <= 256) ? 1 : 2;     // QKV passes: q|k|v (N = 192) or q|k (256) + v (128)
-  constexpr int NUP = (4 * DC) / 256;              // MLP-up passes of N = 256
+  constexpr int NC = DC / 4;                       // residual-stream columns per compute thread
   constexpr int TB = kT * DC * 2;                  // bytes of this CTA's Q (or K, or V) tiles, all local heads
+  constexpr int OWN = DC / 64;                     // A-operand chunks this CTA produces
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* RA = smem;                                          // resident A operand | Q,K,V,P tiles | streamed A slots
   uint8_t* ring = RA + p.ra_bytes;                             // weight stages
-  uint8_t* misc = ring + p.stages * kStageBytes;
+  uint8_t* misc = ring + p.stages * p.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);
   uint64_t* bfull = bars;                                      // [8]
-  uint64_t* bempty = bars + kMaxStages;                        // [8]
-  uint64_t* afull = bars + 2 * kMaxStages;                     // [8]
-  uint64_t* aempty = bars + 2 * kMaxStages + kMaxASlots;       // [8]
-  uint64_t* acc_bar = bars + 2 * kMaxStages + 2 * kMaxASlots;  // [2]
-  uint64_t* op_bar = acc_bar + 2;                              // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_bar + 1);
-  float* smax = reinterpret_cast<float*>(misc + 512);          // [2][128]
-  float* ssum = smax + 2 * kT;                                 // [2][128]
-  float2* stats = reinterpret_cast<float2*>(misc + 512 + 2048);   // [2C][128] LayerNorm partial (sum, sum of squares)
+  uint64_t* bempty = bfull + kMaxStages;                       // [8]
+  uint64_t* afull = bempty + kMaxStages;                       // [10]
+  uint64_t* aempty = afull + kMaxASlots;                       // [10]
+  uint64_t* acc_bar = aempty + kMaxASlots;                     // [4]  GEMM accumulators (round robin: <= 4 passes in flight)
+  uint64_t* tiles_bar = acc_bar + 4;                           // [1]  Q, K, V tiles written
+  uint64_t* p_bar = tiles_bar + 1;                             // [2]  P of group g written (S consumed)
+  uint64_t* s_bar = p_bar + 2;                                 // [2]  S of group g ready
+  uint64_t* o_bar = s_bar + 2;                                 // [2]  O of group g ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
+  float* smax = reinterpret_cast<float*>(misc + 512);          // [4][128]  (group * 2 + half)
+  float* ssum = smax + 4 * kT;                                 // [4][128]
+  float2* part = reinterpret_cast<float2*>(misc + 512 + 4096);     // [4][128] LayerNorm partials of the column quarters
+  float2* stats = part + 4 * kT;                               // [2][C][128] per-CTA partial (sum, sum of squares)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C, d = p.d;
   const int rank = static_cast<int>(cluster_ctarank());
   const int cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+  const int kch_d = d / 64;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&maps.wqkv);
-    prefetch_tmap(&maps.wo);
-    prefetch_tmap(&maps.w1);
-    prefetch_tmap(&maps.w2);
-    prefetch_tmap(&maps.abuf);
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&maps.w[i]);
     prefetch_tmap(&maps.hbuf);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bfull[i], 1);
@@ -175,21 +137,26 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
       mbar_init(&afull[i], 1);
       mbar_init(&aempty[i], 1);
     }
-    mbar_init(&acc_bar[0], 1);
-    mbar_init(&acc_bar[1], 1);
-    mbar_init(op_bar, kComputeWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&acc_bar[i], 1);
+    mbar_init(tiles_bar, kComputeWarps);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&p_bar[g], kComputeWarps / 2);
+      mbar_init(&s_bar[g], 1);
+      mbar_init(&o_bar[g], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
-  // peers write LayerNorm partials into this CTA's shared memory: nobody may run ahead of a CTA that has not started
+  // peers write into this CTA's shared memory (LN partials, operand chunks): nobody may run ahead of a CTA that has
+  // not initialised its barriers yet
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // (no early launch_dependents: a dependent kernel must not take SMs from clusters still to be scheduled)
 
-  const int k32_d = d / 32, kch_d = d / 64;
-  const int cpi = 2 + 6 * p.layers;               // cluster barriers per image
+  const int cpi = 1 + 4 * p.layers;               // cluster barriers per image
+  const int n_passes = p.npass_qkv + p.npass_up + 2;
 
   if (warp == 0) {
     // ===================================================== weight (B) producer
@@ -202,144 +169,156 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
     };
     for (int b = cluster_id; b < p.B; b += n_clusters) {
       sp();
-      sp();
       for (int l = 0; l < p.layers; ++l) {
-        const int rq = l * 3 * d + rank * DC;
-        if (NQP == 1) {
-          produce_pass(&maps.wqkv, 3, rq, rq + d, rq + 2 * d, DC, k32_d, ring, bfull, bempty, p.stages, r);
-        } else {
-          produce_pass(&maps.wqkv, 2, rq, rq + d, 0, DC, k32_d, ring, bfull, bempty, p.stages, r);
-          produce_pass(&maps.wqkv, 1, rq + 2 * d, 0, 0, DC, k32_d, ring, bfull, bempty, p.stages, r);
+        for (int pi = 0; pi < n_passes; ++pi) {
+          const Pass& ps = p.passes[pi];
+          const CUtensorMap* map = &maps.w[ps.map];
+          const int row_off = rank * ps.cta_stride + l * ps.layer_stride;
+          const uint32_t sub_bytes = static_cast<uint32_t>(ps.n) * 128u;
+          const uint32_t tx = sub_bytes * static_cast<uint32_t>(ps.kpack);
+          for (int s = 0; s < ps.kchunks / ps.kpack; ++s) {
+            mbar_wait(&bempty[r.stage], r.phase ^ 1u);
+            if (elect_one_sync()) {
+              uint8_t* dst = ring + r.stage * p.stage_bytes;
+              mbar_arrive_expect_tx(&bfull[r.stage], tx);
+              for (int j = 0; j < ps.kpack; ++j)
+                for (int sg = 0; sg < ps.nseg; ++sg)
+                  tma_load_2d(dst + j * sub_bytes + sg * ps.seg_rows * 128, map, &bfull[r.stage], (s * ps.kpack + j) * 64,
+                              ps.row[sg] + row_off);
+            }
+            __syncwarp();
+            ring_advance(r, p.stages);
+          }
+          // barriers that follow this pass in program order: after QKV (#A), out (#B), the last up pass (#D), down (#E)
+          if (pi == p.npass_qkv - 1 || pi == p.npass_qkv || pi == p.npass_qkv + p.npass_up || pi == n_passes - 1) sp();
         }
-        sp();                                                                              // #A
-        produce_pass(&maps.wo, 1, l * d + rank * DC, 0, 0, DC, k32_d, ring, bfull, bempty, p.stages, r);
-        sp();                                                                              // #B
-        sp();                                                                              // #C
-        for (int u = 0; u < NUP; ++u)
-          produce_pass(&maps.w1, 1, l * 4 * d + rank * 4 * DC + u * 256, 0, 0, 256, k32_d, ring, bfull, bempty,
-                       p.stages, r);
-        sp();                                                                              // #D
-        produce_pass(&maps.w2, 1, l * d + rank * DC, 0, 0, DC, 4 * k32_d, ring, bfull, bempty, p.stages, r);
-        sp();                                                                              // #E
-        sp();                                                                              // #F
       }
     }
     if (pend) cluster_wait_acquire();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     Ring r{0, 0u};
-    uint32_t a_par = 0u;
-    uint32_t ev = 0u, opn = 0u;
+    uint32_t a_par = 0u, ev = 0u;
+    uint32_t tiles_n = 0u, pair_n = 0u;
     bool pend = false;
     auto sp = [&]() {
       if (pend) cluster_wait_acquire();
       cluster_arrive_release();
       pend = true;
     };
-    auto acc = [&]() -> uint64_t* { return &acc_bar[(ev++) & 1u]; };
     const uint32_t ra_addr = smem_u32(RA), ring_addr = smem_u32(ring);
     const uint32_t tile_b = static_cast<uint32_t>(kT * p.dk * 2);           // one head's Q (or K, V) tile
     const uint32_t rowB = static_cast<uint32_t>(p.rowB);
     const uint32_t chunk_b = static_cast<uint32_t>(kT) * rowB;
     const uint32_t idesc_s = umma_idesc_ex(128, 128, 0, 0);
     const uint32_t idesc_o = umma_idesc_ex(128, static_cast<uint32_t>(p.dk), 0, 1);
-    auto issue_s = [&](int h) {
+    constexpr uint32_t op_hi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, SWIZZLE_128B
+    auto issue_s = [&](int h, int g) {        // S(h) -> TMEM columns [384 - 128 g, +128)
       if (elect_one_sync()) {
-        const uint32_t q0 = ra_addr + static_cast<uint32_t>(h) * tile_b, k0 = q0 + TB;
+        const uint32_t q0 = ra_addr + static_cast<uint32_t>(h) * 2u * tile_b, k0 = q0 + tile_b;
         int kk = 0;
         for (int ci = 0; ci < p.nch; ++ci)
           for (int k = 0; k < p.cw / 16; ++k, ++kk) {
             const uint64_t da = umma_desc(q0 + ci * chunk_b + k * 32, 0, 8u * rowB, p.layout);
             const uint64_t db = umma_desc(k0 + ci * chunk_b + k * 32, 0, 8u * rowB, p.layout);
-            umma_bf16(tmem_base + kTmemS, da, db, idesc_s, kk > 0 ? 1u : 0u);
+            umma_bf16(tmem_base + 384u - 128u * g, da, db, idesc_s, kk > 0 ? 1u : 0u);
           }
-        umma_commit(acc());
-      } else {
-        ++ev;
+        umma_commit(&s_bar[g]);
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int h) {
+    auto issue_pv = [&](int h, int g) {       // O(h) -> TMEM columns [128 g, +dk)
       if (elect_one_sync()) {
-        const uint32_t v0 = ra_addr + 2u * TB + static_cast<uint32_t>(h) * tile_b, p0 = ra_addr + 3u * TB;
+        const uint32_t v0 = ra_addr + 2u * TB + static_cast<uint32_t>(h) * tile_b;
+        const uint32_t p0 = p.p_off >= 0 ? ra_addr + static_cast<uint32_t>(p.p_off) + static_cast<uint32_t>(g) * (kT * 256)
+                                         : ra_addr + static_cast<uint32_t>(h) * 2u * tile_b;
         for (int k = 0; k < kT / 16; ++k) {
           const uint64_t da = umma_desc(p0 + (k >> 2) * (kT * 128) + (k & 3) * 32, 0, 1024, 2);
           const uint64_t db = umma_desc(v0 + k * 16 * rowB, chunk_b, 8u * rowB, p.layout);
-          umma_bf16(tmem_base, da, db, idesc_o, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + 128u * g, da, db, idesc_o, k > 0 ? 1u : 0u);
         }
-        umma_commit(acc());
-      } else {
-        ++ev;
+        umma_commit(&o_bar[g]);
       }
       __syncwarp();
     };
-    auto gemm = [&](int a_mode, int n, int k32, uint32_t tcol) {
-      uint64_t* ab = &acc_bar[ev & 1u];
+    auto gemm = [&](const Pass& ps) {
+      uint64_t* ab = &acc_bar[ev & 3u];
       ++ev;
-      mma_pass(ra_addr, ring_addr, a_mode, n, k32, tmem_base + tcol, afull, aempty, p.a_slots, a_par, bfull, bempty,
-               p.stages, r, ab);
+      const uint32_t idesc = umma_idesc_ex(128u, static_cast<uint32_t>(ps.n), 0, 0);
+      const uint32_t sub16 = (static_cast<uint32_t>(ps.n) * 128u) >> 4;
+      const int n_stage = ps.kchunks / ps.kpack;
+      for (int s = 0; s < n_stage; ++s) {
+        mbar_wait(&bfull[r.stage], r.phase);
+        const uint32_t b_lo0 = (ring_addr + static_cast<uint32_t>(r.stage) * p.stage_bytes) >> 4;
+        for (int j = 0; j < ps.kpack; ++j) {
+          const int chunk = s * ps.kpack + j;
+          const int slot = ps.a_mode == 2 ? chunk % p.a_slots : chunk;
+          if (ps.a_mode != 1) {
+            mbar_wait(&afull[slot], (a_par >> slot) & 1u);
+            a_par ^= 1u << slot;
+          }
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t a_lo = (ra_addr + static_cast<uint32_t>(slot) * kAChunk) >> 4;
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(j) * sub16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {          // four K = 16 steps per 64-wide chunk (+32 B inside the swizzle atom)
+              const uint64_t da = (static_cast<uint64_t>(op_hi) << 32) | ((a_lo + 2u * k) & 0x3FFFu);
+              const uint64_t db = (static_cast<uint64_t>(op_hi) << 32) | ((b_lo + 2u * k) & 0x3FFFu);
+              umma_bf16(tmem_base + static_cast<uint32_t>(ps.tcol), da, db, idesc, (chunk | k) != 0 ? 1u : 0u);
+            }
+            if (ps.a_mode == 2) umma_commit(&aempty[slot]);
+            if (j == ps.kpack - 1) {
+              umma_commit(&bempty[r.stage]);
+              if (s == n_stage - 1) umma_commit(ab);
+            }
+          }
+          __syncwarp();
+        }
+        ring_advance(r, p.stages);
+      }
     };
     for (int b = cluster_id; b < p.B; b += n_clusters) {
       sp();
-      sp();
       for (int l = 0; l < p.layers; ++l) {
-        if (NQP == 1) {
-          gemm(0, 3 * DC, k32_d, 0);
-        } else {
-          gemm(0, 256, k32_d, 0);
-          gemm(1, 128, k32_d, 256);
-        }
-        // attention: S(h+1) is issued right behind PV(h), so it runs while the compute warps drain O(h)
-        mbar_wait(op_bar, (opn++) & 1u);      // Q, K, V tiles written
+        int pi = 0;
+        for (; pi < p.npass_qkv; ++pi) gemm(p.passes[pi]);
+        // attention, two heads at a time (group g = the compute warps that own the head)
+        mbar_wait(tiles_bar, (tiles_n++) & 1u);          // Q, K, V tiles written
         tc_fence_after();
-        issue_s(0);
-        for (int h = 0; h < p.hpc; ++h) {
-          mbar_wait(op_bar, (opn++) & 1u);    // P(h) written, S(h) consumed
-          tc_fence_after();
-          issue_pv(h);
-          if (h + 1 < p.hpc) issue_s(h + 1);
+        for (int pr = 0; pr < HP; ++pr) {
+          issue_s(2 * pr, 0);
+          issue_s(2 * pr + 1, 1);
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&p_bar[g], pair_n & 1u);           // P written, S consumed, O of the previous pair read out
+            tc_fence_after();
+            issue_pv(2 * pr + g, g);
+          }
+          ++pair_n;
         }
-        sp();                                 // #A
-        gemm(0, DC, k32_d, 0);                // out-proj
-        sp();                                 // #B
-        sp();                                 // #C
-        for (int u = 0; u < NUP; ++u) gemm(u == 0 ? 0 : 1, 256, k32_d, static_cast<uint32_t>(u) * 256u);
-        sp();                                 // #D
-        gemm(2, DC, 4 * k32_d, 0);            // down-proj, A streamed
-        sp();                                 // #E
-        sp();                                 // #F
+        sp();                                            // #A
+        gemm(p.passes[pi++]);                            // out-proj
+        sp();                                            // #B
+        for (int u = 0; u < p.npass_up; ++u) gemm(p.passes[pi++]);
+        sp();                                            // #D
+        gemm(p.passes[pi++]);                            // down-proj, A streamed
+        sp();                                            // #E
       }
     }
     if (pend) cluster_wait_acquire();
   } else if (warp == 2) {
-    // ===================================================== activation (A) producer
+    // ===================================================== streamed-A producer (hidden -> operand slots)
     uint32_t e_par = 0u;
     auto cb = [&]() {
       cluster_arrive_release();
       cluster_wait_acquire();
     };
-    auto load_resident = [&](int buf, int b) {
-      if (elect_one_sync()) {
-        fence_proxy_async_all();
-        const int row = (buf * p.B + b) * kT;
-        for (int j = 0; j < kch_d; ++j) {
-          mbar_arrive_expect_tx(&afull[j], kAChunk);
-          tma_load_2d(RA + j * kAChunk, &maps.abuf, &afull[j], j * 64, row);
-        }
-      }
-      __syncwarp();
-    };
     for (int b = cluster_id; b < p.B; b += n_clusters) {
       cb();
-      cb();
-      load_resident(0, b);                    // LN1(x) of layer 0
       for (int l = 0; l < p.layers; ++l) {
         cb();                                 // #A
-        load_resident(1, b);                  // O
         cb();                                 // #B
-        cb();                                 // #C
-        load_resident(2, b);                  // LN2(x)
-        cb();                                 // #D: hidden published -> stream it through the operand slots
+        cb();                                 // #D: hidden published
         for (int ch = 0; ch < 4 * kch_d; ++ch) {
           const int slot = ch % p.a_slots;
           mbar_wait(&aempty[slot], ((e_par >> slot) & 1u) ^ 1u);
@@ -352,8 +331,6 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
           __syncwarp();
         }
         cb();                                 // #E
-        cb();                                 // #F
-        if (l + 1 < p.layers) load_resident(0, b);
       }
     }
   } else if (warp == 3) {
@@ -363,89 +340,138 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
       cluster_wait_acquire();
     }
   } else {
-    // ===================================================== compute warps: thread (t, hh)
+    // ===================================================== compute warps: thread (t, qd)
     const int q = warp & 3;                 // TMEM lane quarter
-    const int hh = (warp - 4) >> 2;         // column half
+    const int qd = (warp - 4) >> 2;         // column quarter
+    const int grp = qd >> 1, hh = qd & 1;   // attention: head group, half of the head's columns / keys
     const int t = q * 32 + lane;            // token row
+    const int ctid = threadIdx.x - 128;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const int col0 = rank * DC + hh * NC;   // first residual-stream column of this thread
+    const int col0 = rank * DC + qd * NC;   // first residual-stream column of this thread
     const int dk = p.dk, rowB = p.rowB, cw = p.cw;
     const int swz = p.layout == 2 ? (t & 7) : (p.layout == 4 ? ((t >> 1) & 3) : ((t >> 2) & 1));
     const int tile_b = kT * dk * 2;
-    uint32_t ev = 0u;
+    uint32_t ev = 0u, pair_n = 0u, sbuf = 0u;
     float xv[NC];
+    int cur_l = 0;
+    auto mark = [&](int slot) {
+      if (p.trace != nullptr && warp == 4 && lane == 0)
+        p.trace[(static_cast<size_t>(blockIdx.x) * p.layers + cur_l) * 16 + slot] = static_cast<unsigned long long>(clock64());
+    };
     auto acc_wait = [&]() {
-      mbar_wait(&acc_bar[ev & 1u], (ev >> 1) & 1u);
+      mbar_wait(&acc_bar[ev & 3u], (ev >> 2) & 1u);
       ++ev;
+      tc_fence_after();
     };
     auto cb = [&]() {
       cluster_arrive_release();
       cluster_wait_acquire();
     };
-    // LayerNorm of the cluster-distributed rows: partial sums to every CTA (DSMEM), normalise the own slice.
-    // dst_bf16 != null: bf16 operand slice for the next GEMM (published by the second barrier); else fp32 output.
-    auto ln_step = [&](const float* gamma, const float* beta, float eps, __nv_bfloat16* dst_bf16, float* dst_f32) {
+    // own-chunk address of (row t, column c of this CTA's slice): K-major SWIZZLE_128B chunk layout
+    auto own_chunk_ptr = [&](int c) -> uint8_t* {
+      return RA + (rank * OWN + (c >> 6)) * kAChunk + t * 128 + ((((c & 63) >> 3) ^ (t & 7)) << 4);
+    };
+    // Called by all compute threads right after a cluster barrier that guarantees every CTA's operand slots are free.
+    auto arm_chunks = [&]() {
+      if (ctid == 0)
+        for (int j = 0; j < kch_d; ++j)
+          if (j / OWN != rank) mbar_arrive_expect_tx(&afull[j], kAChunk);
+    };
+    // This CTA's chunk(s) are written: hand them to the local MMA issuer and push them into every peer.
+    auto publish_chunks = [&]() {
+      fence_proxy_async();
+      named_bar_sync(3, kCompute);
+      if (ctid == 0) {
+        for (int o = 0; o < OWN; ++o) {
+          const int j = rank * OWN + o;
+          mbar_arrive(&afull[j]);
+          const uint32_t src = smem_u32(RA + j * kAChunk), bar = smem_u32(&afull[j]);
+          for (int r = 0; r < C; ++r)
+            if (r != rank) bulk_copy_s2c(mapa_u32(src, static_cast<uint32_t>(r)), src, kAChunk, mapa_u32(bar, static_cast<uint32_t>(r)));
+        }
+      }
+    };
+    // LayerNorm of the cluster-distributed rows.  dst_f32 == null: the normalised slice becomes the next A operand.
+    auto ln_step = [&](const float* gamma, const float* beta, float eps, float* dst_f32, int mk) {
       float s = 0.f, sq = 0.f;
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         s += xv[i];
         sq = fmaf(xv[i], xv[i], sq);
       }
-      const uint32_t laddr = smem_u32(&stats[(rank * 2 + hh) * kT + t]);
-      for (int r = 0; r < C; ++r) st_cluster_v2f32(mapa_u32(laddr, static_cast<uint32_t>(r)), s, sq);
+      part[qd * kT + t] = make_float2(s, sq);
+      // gamma / beta of this thread's columns: issue the loads before the barriers
+      float4 gg[NC / 4], bb[NC / 4];
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) {
+        gg[i] = __ldg(reinterpret_cast<const float4*>(gamma + col0) + i);
+        bb[i] = __ldg(reinterpret_cast<const float4*>(beta + col0) + i);
+      }
+      named_bar_sync(3, kCompute);
+      if (qd == 0) {
+        const float2 a0 = part[t], a1 = part[kT + t], a2 = part[2 * kT + t], a3 = part[3 * kT + t];
+        const float cs = (a0.x + a1.x) + (a2.x + a3.x), cq = (a0.y + a1.y) + (a2.y + a3.y);
+        const uint32_t laddr = smem_u32(&stats[(sbuf * C + rank) * kT + t]);
+        for (int r = 0; r < C; ++r) st_cluster_v2f32(mapa_u32(laddr, static_cast<uint32_t>(r)), cs, cq);
+      }
       cb();
+      mark(mk);
+      if (dst_f32 == nullptr) arm_chunks();
       float S = 0.f, Q = 0.f;
-      for (int j = 0; j < 2 * C; ++j) {
-        const float2 v = stats[j * kT + t];
+      for (int j = 0; j < C; ++j) {
+        const float2 v = stats[(sbuf * C + j) * kT + t];
         S += v.x;
         Q += v.y;
       }
+      sbuf ^= 1u;
       const float inv_d = 1.0f / static_cast<float>(d);
       const float mean = S * inv_d;
       const float var = fmaxf(Q * inv_d - mean * mean, 0.f);
       const float rstd = rsqrtf(var + eps);
-      const float4* g4 = reinterpret_cast<const float4*>(gamma + col0);
-      const float4* b4 = reinterpret_cast<const float4*>(beta + col0);
 #pragma unroll
       for (int i = 0; i < NC; i += 8) {
         float f[8];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const float4 gg = __ldg(g4 + (i >> 2) + j), bb = __ldg(b4 + (i >> 2) + j);
-          f[4 * j + 0] = (xv[i + 4 * j + 0] - mean) * rstd * gg.x + bb.x;
-          f[4 * j + 1] = (xv[i + 4 * j + 1] - mean) * rstd * gg.y + bb.y;
-          f[4 * j + 2] = (xv[i + 4 * j + 2] - mean) * rstd * gg.z + bb.z;
-          f[4 * j + 3] = (xv[i + 4 * j + 3] - mean) * rstd * gg.w + bb.w;
+          const float4 g4 = gg[(i >> 2) + j], b4 = bb[(i >> 2) + j];
+          f[4 * j + 0] = (xv[i + 4 * j + 0] - mean) * rstd * g4.x + b4.x;
+          f[4 * j + 1] = (xv[i + 4 * j + 1] - mean) * rstd * g4.y + b4.y;
+          f[4 * j + 2] = (xv[i + 4 * j + 2] - mean) * rstd * g4.z + b4.z;
+          f[4 * j + 3] = (xv[i + 4 * j + 3] - mean) * rstd * g4.w + b4.w;
         }
-        if (dst_bf16 != nullptr) {
-          *reinterpret_cast<bf16x8*>(dst_bf16 + i) = pack8(f);
+        if (dst_f32 == nullptr) {
+          *reinterpret_cast<bf16x8*>(own_chunk_ptr(qd * NC + i)) = pack8(f);
         } else {
           *reinterpret_cast<float4*>(dst_f32 + i) = make_float4(f[0], f[1], f[2], f[3]);
           *reinterpret_cast<float4*>(dst_f32 + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
         }
       }
-      fence_proxy_async_all();
-      cb();
+      if (dst_f32 == nullptr) publish_chunks();
+      mark(mk + 1);
     };
     // x += accumulator + bias  (out-proj / down-proj epilogue; accumulator columns [0, DC))
-    auto residual_epilogue = [&](const float* bias) {
+    auto residual_epilogue = [&](const float* bias, int mk) {
+      float4 bv[NC / 4];
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
       acc_wait();
-      tc_fence_after();
+      mark(mk);
 #pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_addr + static_cast<uint32_t>(hh * NC + c0), v);
-        const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + c0);
+      for (int c0 = 0; c0 < NC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16_nowait(tmem_base + lane_addr + static_cast<uint32_t>(qd * NC + c0), v);
+        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + i);
-          xv[c0 + 4 * i + 0] += __uint_as_float(v[4 * i + 0]) + bb.x;
-          xv[c0 + 4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bb.y;
-          xv[c0 + 4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bb.z;
-          xv[c0 + 4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bb.w;
+        for (int i = 0; i < 4; ++i) {
+          const float4 b4 = bv[(c0 >> 2) + i];
+          xv[c0 + 4 * i + 0] += __uint_as_float(v[4 * i + 0]) + b4.x;
+          xv[c0 + 4 * i + 1] += __uint_as_float(v[4 * i + 1]) + b4.y;
+          xv[c0 + 4 * i + 2] += __uint_as_float(v[4 * i + 2]) + b4.z;
+          xv[c0 + 4 * i + 3] += __uint_as_float(v[4 * i + 3]) + b4.w;
         }
       }
       tc_fence_before();
+      mark(mk + 1);
     };
 
     for (int b = cluster_id; b < p.B; b += n_clusters) {
@@ -461,32 +487,31 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
           xv[4 * i + 3] = v.w;
         }
       }
-      __nv_bfloat16* a_ln1 = p.abuf + (static_cast<size_t>(0) * p.B * kT + row) * d + col0;
-      __nv_bfloat16* a_o = p.abuf + (static_cast<size_t>(1) * p.B * kT + row) * d + rank * DC;
-      __nv_bfloat16* a_ln2 = p.abuf + (static_cast<size_t>(2) * p.B * kT + row) * d + col0;
-      ln_step(p.ln1g, p.ln1b, p.eps1, a_ln1, nullptr);
+      ln_step(p.ln1g, p.ln1b, p.eps1, nullptr, 14);
 
       for (int l = 0; l < p.layers; ++l) {
+        cur_l = l;
+        mark(0);
         // ---------------- QKV accumulator -> Q / K / V operand tiles (they overwrite the dead LN1(x) operand)
-        for (int z = 0; z < NQP; ++z) acc_wait();
-        tc_fence_after();
+        for (int z = 0; z < p.npass_qkv; ++z) acc_wait();
+        mark(1);
         {
           const float* bq = p.bqkv + l * 3 * d + rank * DC;
 #pragma unroll 1
-          for (int z = 0; z < NQP; ++z) {
-            const int n = NQP == 1 ? 3 * DC : (z == 0 ? 256 : 128);
-            const int g0 = z == 0 ? 0 : 256;                    // first q|k|v column of the pass (= its TMEM column)
+          for (int z = 0; z < p.npass_qkv; ++z) {
+            const int n = p.passes[z].n, g0 = p.passes[z].tcol;    // first q|k|v column of the pass = its TMEM column
 #pragma unroll 1
-            for (int c0 = hh * (n / 2); c0 < (hh + 1) * (n / 2); c0 += 32) {
-              const int g = g0 + c0;                            // column within this CTA's [q | k | v], multiple of 32
-              uint32_t v[32];
-              tmem_ld32(tmem_base + lane_addr + static_cast<uint32_t>(g), v);
-              const int part = g / DC, m0 = g - part * DC;
-              const float4* b4 = reinterpret_cast<const float4*>(bq + part * d + m0);
-              uint8_t* part_base = RA + part * TB;
+            for (int c0 = qd * (n >> 2); c0 < (qd + 1) * (n >> 2); c0 += 16) {
+              const int g = g0 + c0;                               // column within this CTA's [q | k | v], multiple of 16
+              uint32_t v[16];
+              tmem_ld16_nowait(tmem_base + lane_addr + static_cast<uint32_t>(g), v);
+              const int pt = g / DC, m0 = g - pt * DC;
+              const float4* b4 = reinterpret_cast<const float4*>(bq + pt * d + m0);
+              const float4 bA = __ldg(b4), bB = __ldg(b4 + 1), bC = __ldg(b4 + 2), bD = __ldg(b4 + 3);
+              tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 b0 = __ldg(b4 + 2 * j), b1 = __ldg(b4 + 2 * j + 1);
+              for (int j = 0; j < 2; ++j) {
+                const float4 b0 = j == 0 ? bA : bC, b1 = j == 0 ? bB : bD;
                 float f[8];
                 f[0] = __uint_as_float(v[8 * j + 0]) + b0.x;
                 f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
@@ -499,8 +524,9 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
                 const int m = m0 + 8 * j;
                 const int head = m / dk, e = m - head * dk;
                 const int ci = e / cw, ec = e - ci * cw;
-                uint8_t* dst = part_base + head * tile_b + ci * (kT * rowB) + t * rowB + (((ec >> 3) ^ swz) << 4);
-                *reinterpret_cast<bf16x8*>(dst) = pack8(f);
+                // Q(h) | K(h) interleaved per head, then the V tiles
+                uint8_t* tile = pt == 2 ? RA + 2 * TB + head * tile_b : RA + head * 2 * tile_b + pt * tile_b;
+                *reinterpret_cast<bf16x8*>(tile + ci * (kT * rowB) + t * rowB + (((ec >> 3) ^ swz) << 4)) = pack8(f);
               }
             }
           }
@@ -508,97 +534,128 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(op_bar);
+        if (lane == 0) mbar_arrive(tiles_bar);
+        mark(2);
 
-        // ---------------- attention over the local heads
-        for (int h = 0; h < p.hpc; ++h) {
-          acc_wait();                                  // S(h)
+        // ---------------- attention: this thread's group handles head 2 pr + grp of every pair
+        uint4 opk[HP][4];                                   // O / rowsum of this thread, bf16 packed (<= 32 values a pair)
+#pragma unroll
+        for (int pr = 0; pr < HP; ++pr) {
+          const int h = 2 * pr + grp;
+          const uint32_t par = pair_n & 1u;
+          ++pair_n;
+          mbar_wait(&s_bar[grp], par);                 // S(h)
           tc_fence_after();
           float sum = 0.f;
           {
-            uint32_t v0[32], v1[32];
-            tmem_ld32(tmem_base + lane_addr + kTmemS + static_cast<uint32_t>(hh * 64), v0);
-            tmem_ld32(tmem_base + lane_addr + kTmemS + static_cast<uint32_t>(hh * 64 + 32), v1);
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            const uint32_t s_addr = tmem_base + lane_addr + 384u - 128u * grp + static_cast<uint32_t>(hh * 64);
+            tmem_ld16_nowait(s_addr, v0);
+            tmem_ld16_nowait(s_addr + 16, v1);
+            tmem_ld16_nowait(s_addr + 32, v2);
+            tmem_ld16_nowait(s_addr + 48, v3);
+            tmem_wait_ld();
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-            smax[hh * kT + t] = mx;
-            named_bar_sync(1, 32 * kComputeWarps);
-            mx = fmaxf(mx, smax[(hh ^ 1) * kT + t]);
+            for (int i = 0; i < 16; ++i)
+              mx = fmaxf(fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i]))),
+                         fmaxf(__uint_as_float(v2[i]), __uint_as_float(v3[i])));
+            smax[(grp * 2 + hh) * kT + t] = mx;
+            named_bar_sync(1 + grp, kCompute / 2);
+            mx = fmaxf(mx, smax[(grp * 2 + (hh ^ 1)) * kT + t]);
             const float mxs = mx * p.scale_log2e;
-            uint8_t* prow = RA + 3 * TB + hh * (kT * 128) + t * 128;     // P chunk hh (64 keys), row = query
+            uint8_t* ptile = p.p_off >= 0 ? RA + p.p_off + grp * (kT * 256) : RA + h * 2 * tile_b;
+            uint8_t* prow = ptile + hh * (kT * 128) + t * 128;           // P chunk hh (64 keys), row = query
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const uint32_t raw = j < 4 ? v0[8 * j + i] : v1[8 * (j - 4) + i];
+                const uint32_t raw = j < 2 ? v0[8 * j + i] : (j < 4 ? v1[8 * (j - 2) + i] : (j < 6 ? v2[8 * (j - 4) + i] : v3[8 * (j - 6) + i]));
                 const float e = exp2f(fmaf(__uint_as_float(raw), p.scale_log2e, -mxs));
                 f[i] = __bfloat162float(__float2bfloat16_rn(e));
                 sum += f[i];                               // normalise by what the MMA will see
               }
               *reinterpret_cast<bf16x8*>(prow + ((j ^ (t & 7)) << 4)) = pack8(f);
             }
-            ssum[hh * kT + t] = sum;
+            ssum[(grp * 2 + hh) * kT + t] = sum;
           }
           fence_proxy_async();
           tc_fence_before();
-          named_bar_sync(1, 32 * kComputeWarps);          // partner's row sum visible; all S reads retired
-          if (lane == 0) mbar_arrive(op_bar);
-          acc_wait();                                  // O(h)
+          named_bar_sync(1 + grp, kCompute / 2);          // partner's row sum visible; all S reads of the group retired
+          if (lane == 0) mbar_arrive(&p_bar[grp]);
+          mbar_wait(&o_bar[grp], par);                 // O(h)
           tc_fence_after();
-          const float inv = 1.0f / (ssum[t] + ssum[kT + t]);
-          __nv_bfloat16* orow = a_o + h * dk;
-          if (dk >= 64) {
-            for (int c0 = 0; c0 < dk / 2; c0 += 32) {
-              uint32_t v[32];
-              tmem_ld32(tmem_base + lane_addr + static_cast<uint32_t>(hh * (dk / 2) + c0), v);
+          const float inv = 1.0f / (ssum[(grp * 2) * kT + t] + ssum[(grp * 2 + 1) * kT + t]);
+          const uint32_t o_addr = tmem_base + lane_addr + 128u * grp;
+          if (dk >= 64) {                              // this thread: columns [hh dk/2, +dk/2) of O: 32 of them (dk = 64)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16_nowait(o_addr + static_cast<uint32_t>(hh * (dk / 2) + c0), v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]) * inv;
-                *reinterpret_cast<bf16x8*>(orow + hh * (dk / 2) + c0 + 8 * j) = pack8(f);
+                const bf16x8 pk = pack8(f);
+                opk[pr][(c0 >> 3) + j] = *reinterpret_cast<const uint4*>(&pk);
               }
             }
-          } else {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + lane_addr, v);
+          } else {                                     // dk = 16 / 32: pieces of 8 columns out of one 16-column load
+            uint32_t v[16];
+            tmem_ld16_nowait(o_addr + static_cast<uint32_t>((hh * (dk / 2)) & ~15), v);
+            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (8 * j >= hh * (dk / 2) && 8 * j < (hh + 1) * (dk / 2)) {
-                float f[8];
+            for (int j = 0; j < 2; ++j) {
+              float f[8];
+              const int src = dk == 16 ? hh : j;       // dk 16: piece hh of the load; dk 32: both pieces
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]) * inv;
-                *reinterpret_cast<bf16x8*>(orow + 8 * j) = pack8(f);
-              }
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(src == 0 ? v[i] : v[8 + i]) * inv;
+              const bf16x8 pk = pack8(f);
+              opk[pr][j] = *reinterpret_cast<const uint4*>(&pk);
             }
           }
           tc_fence_before();
         }
-        fence_proxy_async_all();
-        cb();                                                    // #A: O of every head published
+        mark(3);
+        cb();                                          // #A: every CTA has finished attention -> operand slots free
+        arm_chunks();
+#pragma unroll
+        for (int pr = 0; pr < HP; ++pr) {
+          const int cbase = (2 * pr + grp) * dk + hh * (dk / 2);       // column of this CTA's slice
+          const int npiece = dk >= 64 ? 4 : (dk / 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < npiece) *reinterpret_cast<uint4*>(own_chunk_ptr(cbase + 8 * j)) = opk[pr][j];
+        }
+        publish_chunks();
+        mark(4);
 
         // ---------------- out-proj epilogue + LN2
-        residual_epilogue(p.bo + l * d);
-        ln_step(p.ln2g + l * d, p.ln2b + l * d, p.eps2, a_ln2, nullptr);       // #B, #C
+        residual_epilogue(p.bo + l * d, 5);
+        ln_step(p.ln2g + l * d, p.ln2b + l * d, p.eps2, nullptr, 7);       // #B
 
         // ---------------- MLP up: +bias, erf-GELU -> hidden slice
         {
-          __nv_bfloat16* hrow = p.hbuf + row * (4 * d) + rank * 4 * DC + hh * 128;
-          const float* b1 = p.b1 + l * 4 * d + rank * 4 * DC + hh * 128;
+          const int np = p.npass_max;                           // columns per pass
+          __nv_bfloat16* hrow = p.hbuf + row * (4 * d) + rank * 4 * DC + qd * (np >> 2);
+          const float* b1 = p.b1 + l * 4 * d + rank * 4 * DC + qd * (np >> 2);
 #pragma unroll 1
-          for (int u = 0; u < NUP; ++u) {
+          for (int u = 0; u < p.npass_up; ++u) {
             acc_wait();
-            tc_fence_after();
+            if (u == 0) mark(9);
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-              uint32_t v[32];
-              tmem_ld32(tmem_base + lane_addr + static_cast<uint32_t>(u * 256 + hh * 128 + c0), v);
-              const float4* b4 = reinterpret_cast<const float4*>(b1 + u * 256 + c0);
+            for (int c0 = 0; c0 < (np >> 2); c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16_nowait(tmem_base + lane_addr + static_cast<uint32_t>(u * np + qd * (np >> 2) + c0), v);
+              const float4* b4 = reinterpret_cast<const float4*>(b1 + u * np + c0);
+              const float4 bA = __ldg(b4), bB = __ldg(b4 + 1), bC = __ldg(b4 + 2), bD = __ldg(b4 + 3);
+              tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 b0 = __ldg(b4 + 2 * j), bb1 = __ldg(b4 + 2 * j + 1);
+              for (int j = 0; j < 2; ++j) {
+                const float4 b0 = j == 0 ? bA : bC, bb1 = j == 0 ? bB : bD;
                 float f[8];
                 f[0] = gelu_fast(__uint_as_float(v[8 * j + 0]) + b0.x);
                 f[1] = gelu_fast(__uint_as_float(v[8 * j + 1]) + b0.y);
@@ -608,26 +665,28 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
                 f[5] = gelu_fast(__uint_as_float(v[8 * j + 5]) + bb1.y);
                 f[6] = gelu_fast(__uint_as_float(v[8 * j + 6]) + bb1.z);
                 f[7] = gelu_fast(__uint_as_float(v[8 * j + 7]) + bb1.w);
-                *reinterpret_cast<bf16x8*>(hrow + u * 256 + c0 + 8 * j) = pack8(f);
+                *reinterpret_cast<bf16x8*>(hrow + u * np + c0 + 8 * j) = pack8(f);
               }
             }
           }
           tc_fence_before();
         }
+        mark(10);
         fence_proxy_async_all();
         cb();                                                    // #D: hidden published
+        mark(11);
 
         // ---------------- down-proj epilogue + next LN1 / ln_f
-        residual_epilogue(p.b2 + l * d);
+        residual_epilogue(p.b2 + l * d, 12);
         if (p.dbg != nullptr) {
           float* dp = p.dbg + ((static_cast<size_t>(l) * p.B * kT) + row) * d + col0;
 #pragma unroll
           for (int i = 0; i < NC; ++i) dp[i] = xv[i];
         }
         if (l + 1 < p.layers)
-          ln_step(p.ln1g + (l + 1) * d, p.ln1b + (l + 1) * d, p.eps1, a_ln1, nullptr);     // #E, #F
+          ln_step(p.ln1g + (l + 1) * d, p.ln1b + (l + 1) * d, p.eps1, nullptr, 14);            // #E
         else
-          ln_step(p.lnfg, p.lnfb, p.epsf, nullptr, p.x_out + row * d + col0);              // #E, #F
+          ln_step(p.lnfg, p.lnfb, p.epsf, p.x_out + row * d + col0, 14);                       // #E
       }
     }
   }
@@ -654,7 +713,7 @@ EncodeTiledFn get_encode() {
 }
 
 int encode2d(CUtensorMap* m, const void* base, long long cols, long long rows, int box_cols, int box_rows,
-             CUtensorMapSwizzle swz, const char* what) {
+             const char* what) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -665,7 +724,7 @@ int encode2d(CUtensorMap* m, const void* base, long long cols, long long rows, i
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, str, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s: %lld x %lld, box %d x %d) failed (CUresult %d)", what, rows, cols, box_rows,
@@ -675,62 +734,77 @@ int encode2d(CUtensorMap* m, const void* base, long long cols, long long rows, i
   return CFT_OK;
 }
 
-// Cluster size for (B, d): DC = d / C must be 64 or 128 and C must divide the head count.  Prefer the widest split
-// whose B clusters still fit on the GPU at once (more SMs per image), else the narrowest.
-int pick_cluster(int B, int d, int heads, int forced) {
-  int best = 0;
-  for (int c = 8; c >= 1; c >>= 1) {
-    if (heads % c || d % c) continue;
-    const int dc = d / c;
-    if (dc != 64 && dc != 128) continue;
-    if (forced) {
-      if (c == forced) return c;
-      continue;
-    }
-    if (!best) best = c;                               // widest legal split
-    if (static_cast<long long>(B) * c <= sm_count() - 16) return c;
-    best = c;                                          // remember the narrowest seen so far
-  }
-  return forced ? 0 : best;
-}
-
 struct Plan {
-  int C, DC, ra_bytes, a_slots, stages, smem;
+  int C, DC, hpc, ra_bytes, a_slots, stages, stage_bytes, npass_max, p_off, smem;
 };
+
+// Cluster size for (B, d): DC = d / C must be 64 or 128, every CTA gets 2 or 4 heads (they are processed in pairs).
+// Prefer the widest split whose B clusters fit on the GPU at once (more SMs per image), else the narrowest.
 bool make_plan(int B, int d, int heads, int forced_c, Plan* pl) {
   if (heads <= 0 || d % heads) return false;
   const int dk = d / heads;
-  if (dk != 16 && dk != 32 && dk != 64 && dk != 128) return false;
+  if (dk != 16 && dk != 32 && dk != 64) return false;
   if (d % 64 || d > 512) return false;
-  const int C = pick_cluster(B, d, heads, forced_c);
+  int C = 0, narrowest = 0;
+  for (int c = 8; c >= 1; c >>= 1) {
+    if (heads % c || d % c) continue;
+    const int dc = d / c, hpc = heads / c;
+    if ((dc != 64 && dc != 128) || (hpc != 2 && hpc != 4)) continue;
+    if (forced_c) {
+      if (c == forced_c) C = c;
+      continue;
+    }
+    narrowest = c;
+    if (!C && static_cast<long long>(B) * c <= sm_count() - 16) C = c;
+  }
+  if (!C) C = forced_c ? 0 : narrowest;
   if (!C) return false;
-  const int DC = d / C;
+  const int DC = d / C, hpc = heads / C;
+  const int TB = kT * DC * 2;
   int ra = kT * d * 2;
-  const int tiles = 3 * kT * DC * 2 + 2 * kT * 128;
+  const int tiles = 3 * TB + (dk >= 64 ? 0 : 2 * kT * 256);
   if (tiles > ra) ra = tiles;
   ra = (ra + kAChunk - 1) / kAChunk * kAChunk;
-  const int misc = 512 + 2048 + C * 2 * kT * 8;
-  const int stages_max = (kSmemMax - 1024 - ra - misc) / kStageBytes;
-  if (ra / kAChunk > kMaxASlots || ra / kAChunk < d / 64 || stages_max < 3) return false;
+  const int misc = kMiscFixed + 2 * C * kT * 8;
+  const int ring = kSmemMax - 1024 - ra - misc;
+  if (ra / kAChunk > kMaxASlots || ring < 3 * 16384) return false;
   pl->C = C;
   pl->DC = DC;
+  pl->hpc = hpc;
   pl->ra_bytes = ra;
   pl->a_slots = ra / kAChunk;
-  pl->stages = stages_max > kMaxStages ? kMaxStages : stages_max;
-  pl->smem = 1024 + ra + pl->stages * kStageBytes + misc;
+  pl->stage_bytes = ring >= 3 * 32768 ? 32768 : 16384;
+  pl->npass_max = pl->stage_bytes / 128;
+  pl->stages = ring / pl->stage_bytes;
+  if (pl->stages > kMaxStages) pl->stages = kMaxStages;
+  pl->p_off = dk >= 64 ? -1 : 3 * TB;
+  pl->smem = 1024 + ra + pl->stages * pl->stage_bytes + misc;
   return true;
 }
 
 bool g_attr_set = false;
+unsigned long long* g_trace = nullptr;   // cft_debug_block_trace
 const int g_force_c = getenv("CFT_BLOCK_CLUSTER") ? atoi(getenv("CFT_BLOCK_CLUSTER")) : 0;
+
+template <int DC, int HP>
+cudaError_t launch_block(const cudaLaunchConfig_t& cfg, const BlockMaps& maps, const BlockParams& p) {
+  return cudaLaunchKernelEx(&cfg, cft_gpt_block_kernel<DC, HP>, maps, p);
+}
 
 }  // namespace
 
 using namespace cft;
 
+// Debug timeline: `buf` (device, >= grid * layers * 16 u64) receives clock64 samples of the first compute warp of every CTA
+// for the cft_gpt_block launches that follow; NULL turns it off.  scripts/trace_block.py only.
+extern "C" int cft_debug_block_trace(void* buf) {
+  g_trace = static_cast<unsigned long long*>(buf);
+  return CFT_OK;
+}
+
 extern "C" long long cft_gpt_block_workspace_bytes(int B, int d) {
   if (B <= 0 || d <= 0) return 0;
-  return static_cast<long long>(B) * kT * d * 2 * (3 + 4);
+  return static_cast<long long>(B) * kT * d * 2 * 4;
 }
 
 extern "C" int cft_gpt_block_supported(int B, int d, int heads, int tokens) {
@@ -747,7 +821,8 @@ extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
   CFT_REQUIRE(a->B > 0 && a->layers > 0 && a->tokens == kT, "cft_gpt_block: need B > 0, layers > 0, 128 tokens per image");
   Plan pl;
   if (!make_plan(a->B, a->d, a->heads, a->cluster > 0 ? a->cluster : g_force_c, &pl)) {
-    set_error("cft_gpt_block: shape outside the fused kernel (d %d heads %d): use the per-op path", a->d, a->heads);
+    set_error("cft_gpt_block: shape outside the fused kernel (d %d heads %d cluster %d): use the per-op path", a->d,
+              a->heads, a->cluster);
     return CFT_E_UNSUPPORTED;
   }
   CFT_REQUIRE(a->workspace_bytes >= cft_gpt_block_workspace_bytes(a->B, a->d), "cft_gpt_block: workspace too small");
@@ -756,11 +831,13 @@ extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
                   reinterpret_cast<uintptr_t>(a->w2) % 16 == 0 && reinterpret_cast<uintptr_t>(a->x_in) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(a->x_out) % 16 == 0,
               "cft_gpt_block: misaligned pointer");
-  const int d = a->d, L = a->layers, B = a->B;
+  const int d = a->d, L = a->layers, B = a->B, DC = pl.DC;
   BlockParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.d = d; p.heads = a->heads; p.dk = d / a->heads; p.layers = L; p.C = pl.C; p.hpc = a->heads / pl.C;
-  p.stages = pl.stages; p.a_slots = pl.a_slots; p.ra_bytes = pl.ra_bytes;
+  p.B = B; p.d = d; p.heads = a->heads; p.dk = d / a->heads; p.layers = L; p.C = pl.C; p.hpc = pl.hpc;
+  p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; p.a_slots = pl.a_slots; p.ra_bytes = pl.ra_bytes;
+  p.npass_max = pl.npass_max;
+  p.p_off = pl.p_off;
   p.cw = p.dk < 64 ? p.dk : 64;
   p.nch = p.dk / p.cw;
   p.rowB = p.cw * 2;
@@ -770,27 +847,70 @@ extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
   p.bqkv = a->bqkv; p.bo = a->bo; p.b1 = a->b1; p.b2 = a->b2;
   p.ln1g = a->ln1_g; p.ln1b = a->ln1_b; p.ln2g = a->ln2_g; p.ln2b = a->ln2_b; p.lnfg = a->lnf_g; p.lnfb = a->lnf_b;
   p.x_in = a->x_in; p.x_out = a->x_out;
-  p.abuf = reinterpret_cast<__nv_bfloat16*>(a->workspace);
-  p.hbuf = p.abuf + static_cast<size_t>(3) * B * kT * d;
+  p.hbuf = reinterpret_cast<__nv_bfloat16*>(a->workspace);
   p.dbg = a->debug_x;
+  p.trace = g_trace;
+
+  // ---- the GEMM passes of one layer
+  auto kpack_of = [&](int n, int kchunks) {
+    int kp = pl.stage_bytes / (n * 128);
+    if (kp < 1) kp = 1;
+    while (kp > 1 && kchunks % kp) --kp;
+    return kp;
+  };
+  int np = 0;
+  {   // QKV: whole parts (q, k, v: DC rows each) packed greedily into passes of <= npass_max rows
+    int part = 0;
+    while (part < 3) {
+      int cnt = pl.npass_max / DC;
+      if (cnt < 1) cnt = 1;
+      if (cnt > 3 - part) cnt = 3 - part;
+      Pass& ps = p.passes[np++];
+      ps.map = 0; ps.nseg = cnt; ps.seg_rows = DC;
+      for (int s = 0; s < cnt; ++s) ps.row[s] = (part + s) * d;
+      ps.cta_stride = DC; ps.layer_stride = 3 * d;
+      ps.n = cnt * DC; ps.kchunks = d / 64; ps.kpack = kpack_of(ps.n, ps.kchunks);
+      ps.tcol = part * DC; ps.a_mode = part == 0 ? 0 : 1;
+      part += cnt;
+    }
+    p.npass_qkv = np;
+  }
+  {   // out-proj
+    Pass& ps = p.passes[np++];
+    ps.map = 1; ps.nseg = 1; ps.seg_rows = DC; ps.row[0] = 0; ps.cta_stride = DC; ps.layer_stride = d;
+    ps.n = DC; ps.kchunks = d / 64; ps.kpack = kpack_of(DC, ps.kchunks); ps.tcol = 0; ps.a_mode = 0;
+  }
+  p.npass_up = 4 * DC / pl.npass_max;
+  CFT_REQUIRE(p.npass_up >= 1 && (4 * DC) % pl.npass_max == 0 && np + p.npass_up + 1 <= kMaxPasses,
+              "cft_gpt_block: pass table overflow");
+  for (int u = 0; u < p.npass_up; ++u) {
+    Pass& ps = p.passes[np++];
+    ps.map = 2; ps.nseg = 1; ps.seg_rows = pl.npass_max; ps.row[0] = u * pl.npass_max; ps.cta_stride = 4 * DC;
+    ps.layer_stride = 4 * d;
+    ps.n = pl.npass_max; ps.kchunks = d / 64; ps.kpack = kpack_of(ps.n, ps.kchunks); ps.tcol = u * pl.npass_max;
+    ps.a_mode = u == 0 ? 0 : 1;
+  }
+  {   // down-proj, A streamed
+    Pass& ps = p.passes[np++];
+    ps.map = 3; ps.nseg = 1; ps.seg_rows = DC; ps.row[0] = 0; ps.cta_stride = DC; ps.layer_stride = d;
+    ps.n = DC; ps.kchunks = 4 * d / 64; ps.kpack = kpack_of(DC, ps.kchunks); ps.tcol = 0; ps.a_mode = 2;
+  }
 
   BlockMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
-  if ((rc = encode2d(&maps.wqkv, a->wqkv, d, static_cast<long long>(L) * 3 * d, 32, pl.DC, CU_TENSOR_MAP_SWIZZLE_64B, "wqkv"))) return rc;
-  if ((rc = encode2d(&maps.wo, a->wo, d, static_cast<long long>(L) * d, 32, pl.DC, CU_TENSOR_MAP_SWIZZLE_64B, "wo"))) return rc;
-  if ((rc = encode2d(&maps.w1, a->w1, d, static_cast<long long>(L) * 4 * d, 32, 256, CU_TENSOR_MAP_SWIZZLE_64B, "w1"))) return rc;
-  if ((rc = encode2d(&maps.w2, a->w2, 4 * d, static_cast<long long>(L) * d, 32, pl.DC, CU_TENSOR_MAP_SWIZZLE_64B, "w2"))) return rc;
-  if ((rc = encode2d(&maps.abuf, p.abuf, d, static_cast<long long>(3) * B * kT, 64, kT, CU_TENSOR_MAP_SWIZZLE_128B, "abuf"))) return rc;
-  if ((rc = encode2d(&maps.hbuf, p.hbuf, 4 * d, static_cast<long long>(B) * kT, 64, kT, CU_TENSOR_MAP_SWIZZLE_128B, "hbuf"))) return rc;
+  if ((rc = encode2d(&maps.w[0], a->wqkv, d, static_cast<long long>(L) * 3 * d, 64, DC, "wqkv"))) return rc;
+  if ((rc = encode2d(&maps.w[1], a->wo, d, static_cast<long long>(L) * d, 64, DC, "wo"))) return rc;
+  if ((rc = encode2d(&maps.w[2], a->w1, d, static_cast<long long>(L) * 4 * d, 64, pl.npass_max, "w1"))) return rc;
+  if ((rc = encode2d(&maps.w[3], a->w2, 4 * d, static_cast<long long>(L) * d, 64, DC, "w2"))) return rc;
+  if ((rc = encode2d(&maps.hbuf, p.hbuf, 4 * d, static_cast<long long>(B) * kT, 64, kT, "hbuf"))) return rc;
 
   if (!g_attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(cft_gpt_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax),
-                    "cudaFuncSetAttribute(gpt_block<64>)");
-    if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(cft_gpt_block_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax),
-                    "cudaFuncSetAttribute(gpt_block<128>)");
-    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(cft_gpt_block_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cft_gpt_block_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cft_gpt_block_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cft_gpt_block_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if ((rc = check_cuda(e, "cudaFuncSetAttribute(gpt_block)"))) return rc;
     g_attr_set = true;
   }
   int clusters = B;
@@ -810,8 +930,9 @@ extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = pl.DC == 64 ? cudaLaunchKernelEx(&cfg, cft_gpt_block_kernel<64>, maps, p)
-                              : cudaLaunchKernelEx(&cfg, cft_gpt_block_kernel<128>, maps, p);
+  cudaError_t e;
+  if (DC == 64) e = pl.hpc == 2 ? launch_block<64, 1>(cfg, maps, p) : launch_block<64, 2>(cfg, maps, p);
+  else e = pl.hpc == 2 ? launch_block<128, 1>(cfg, maps, p) : launch_block<128, 2>(cfg, maps, p);
   if (e != cudaSuccess) {
     ls.finish("cft_gpt_block launch");
     return check_cuda(e, "cudaLaunchKernelEx(gpt_block)");

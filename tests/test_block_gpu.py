@@ -52,13 +52,11 @@ def ref_stack(g, x, upto=None):
 
 CASES = [
     # d, layers, B, cluster (0 = auto)
-    (256, 8, 3, 0),       # yolov5l P3: cluster 4, DC 64, dk 32 (SWIZZLE_64B q/k/v tiles)
-    (512, 8, 2, 0),       # yolov5l P4 / yolov5s P5: cluster 4 (B small -> auto may pick 8), dk 64
-    (512, 2, 3, 4),       # DC 128: two QKV passes, two MLP-up passes
-    (512, 2, 3, 8),       # DC 64 with dk 64: one head per CTA
-    (128, 8, 2, 0),       # yolov5s P3: cluster 2, dk 16 (SWIZZLE_32B tiles), 4 heads per CTA
-    (256, 2, 3, 2),       # DC 128 with dk 32: 4 heads per CTA
-    (128, 2, 2, 1),       # a single CTA per image: 8 heads per CTA
+    (256, 8, 3, 0),       # yolov5l P3: cluster 4, DC 64, dk 32 (SWIZZLE_64B q/k/v tiles), 2 heads per CTA
+    (512, 8, 2, 0),       # yolov5l P4 / yolov5s P5: cluster 4, DC 128, dk 64 (P aliases Q|K), 16 KiB weight stages
+    (512, 2, 3, 4),       # the same split forced
+    (128, 8, 2, 0),       # yolov5s P3: cluster 2, dk 16 (SWIZZLE_32B tiles), 4 heads per CTA = two head pairs
+    (256, 2, 3, 2),       # DC 128 with dk 32: 4 heads per CTA, operand region 160 KiB
     (256, 1, 45, 4),      # more images than co-resident clusters: clusters loop over images
 ]
 
