@@ -47,7 +47,7 @@ constexpr int kMaxASlots = 10;
 constexpr int kMaxPasses = 12;
 constexpr int kTmemCols = 512;
 constexpr int kSmemMax = 227 * 1024;
-constexpr int kMiscFixed = 512 + 2048 + 2048 + 4096;   // barriers | softmax max | softmax sum | LN quarter partials
+constexpr int kMiscFixed = 512 + 2048 + 2048;   // barriers | softmax max | softmax sum (= LN quarter partials: never live together)
 
 struct __align__(64) BlockMaps {
   CUtensorMap w[4];               // wqkv, wo, w1, w2: box {64 k, rows}
@@ -75,10 +75,17 @@ struct BlockParams {
   const float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *lnfg, *lnfb;
   const float* x_in;
   float* x_out;
+  const __nv_bfloat16 *wqkv, *wo, *w1, *w2;   // raw weight pointers (L2 prefetch of the next layer)
   __nv_bfloat16* hbuf;            // [B*128][4d]
   float* dbg;                     // optional [layers][B][128][d] dump of x after every layer
-  unsigned long long* trace;      // debug (cft_debug_block_trace): [grid][layers][16] clock64 samples of compute warp 0
+  unsigned long long* trace;      // debug (cft_debug_block_trace): [grid][layers][48] clock64 samples: 0-15 compute warp 0, 16+3i.. MMA issuer pass i {start, first operands landed, last MMA issued}
 };
+
+// one 16-byte store of 8 bf16 (a plain struct copy is split into four 4-byte stores by the compiler)
+__device__ __forceinline__ void st16(void* dst, const float* f) {
+  const bf16x8 pk = pack8(f);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&pk);
+}
 
 struct Ring {
   int stage;
@@ -117,8 +124,9 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
   float* smax = reinterpret_cast<float*>(misc + 512);          // [4][128]  (group * 2 + half)
   float* ssum = smax + 4 * kT;                                 // [4][128]
-  float2* part = reinterpret_cast<float2*>(misc + 512 + 4096);     // [4][128] LayerNorm partials of the column quarters
+  float2* part = reinterpret_cast<float2*>(misc + 512);            // [4][128] LayerNorm partials of the column quarters (aliases smax | ssum)
   float2* stats = part + 4 * kT;                               // [2][C][128] per-CTA partial (sum, sum of squares)
+  float* lpar = reinterpret_cast<float*>(stats + 2 * p.C * kT);  // [13 DC] this layer's biases / LN parameters of the CTA's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C, d = p.d;
@@ -135,7 +143,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
     }
     for (int i = 0; i < kMaxASlots; ++i) {
       mbar_init(&afull[i], 1);
-      mbar_init(&aempty[i], 1);
+      mbar_init(&aempty[i], p.C);      // streamed chunks are multicast: every CTA of the cluster frees the slot
     }
     for (int i = 0; i < 4; ++i) mbar_init(&acc_bar[i], 1);
     mbar_init(tiles_bar, kComputeWarps);
@@ -241,9 +249,15 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
       }
       __syncwarp();
     };
+    int tr_l = 0, tr_pass = 0;
+    auto mmark = [&](int which) {
+      if (p.trace != nullptr && lane == 0 && tr_pass < 10)
+        p.trace[(static_cast<size_t>(blockIdx.x) * p.layers + tr_l) * 48 + 16 + 3 * tr_pass + which] = static_cast<unsigned long long>(clock64());
+    };
     auto gemm = [&](const Pass& ps) {
       uint64_t* ab = &acc_bar[ev & 3u];
       ++ev;
+      mmark(0);
       const uint32_t idesc = umma_idesc_ex(128u, static_cast<uint32_t>(ps.n), 0, 0);
       const uint32_t sub16 = (static_cast<uint32_t>(ps.n) * 128u) >> 4;
       const int n_stage = ps.kchunks / ps.kpack;
@@ -258,6 +272,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
             a_par ^= 1u << slot;
           }
           tc_fence_after();
+          if (s == 0 && j == 0) mmark(1);
           if (elect_one_sync()) {
             const uint32_t a_lo = (ra_addr + static_cast<uint32_t>(slot) * kAChunk) >> 4;
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(j) * sub16;
@@ -267,7 +282,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
               const uint64_t db = (static_cast<uint64_t>(op_hi) << 32) | ((b_lo + 2u * k) & 0x3FFFu);
               umma_bf16(tmem_base + static_cast<uint32_t>(ps.tcol), da, db, idesc, (chunk | k) != 0 ? 1u : 0u);
             }
-            if (ps.a_mode == 2) umma_commit(&aempty[slot]);
+            if (ps.a_mode == 2) umma_commit_mc(&aempty[slot], static_cast<uint16_t>((1u << p.C) - 1u));
             if (j == ps.kpack - 1) {
               umma_commit(&bempty[r.stage]);
               if (s == n_stage - 1) umma_commit(ab);
@@ -277,10 +292,14 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
         }
         ring_advance(r, p.stages);
       }
+      mmark(2);
+      ++tr_pass;
     };
     for (int b = cluster_id; b < p.B; b += n_clusters) {
       sp();
       for (int l = 0; l < p.layers; ++l) {
+        tr_l = l;
+        tr_pass = 0;
         int pi = 0;
         for (; pi < p.npass_qkv; ++pi) gemm(p.passes[pi]);
         // attention, two heads at a time (group g = the compute warps that own the head)
@@ -324,9 +343,11 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
           mbar_wait(&aempty[slot], ((e_par >> slot) & 1u) ^ 1u);
           e_par ^= 1u << slot;
           if (elect_one_sync()) {
+            // all C CTAs stream the same image's hidden: chunk ch is fetched once, by CTA ch % C, and multicast
             if (ch == 0) fence_proxy_async_all();
             mbar_arrive_expect_tx(&afull[slot], kAChunk);
-            tma_load_2d(RA + slot * kAChunk, &maps.hbuf, &afull[slot], ch * 64, b * kT);
+            if (ch % C == rank)
+              tma_load_2d_mc(RA + slot * kAChunk, &maps.hbuf, &afull[slot], ch * 64, b * kT, static_cast<uint16_t>((1u << C) - 1u));
           }
           __syncwarp();
         }
@@ -334,10 +355,35 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
       }
     }
   } else if (warp == 3) {
-    const int n_img = (p.B - cluster_id + n_clusters - 1) / n_clusters;
-    for (int i = 0; i < n_img * cpi; ++i) {
+    // ===================================================== L2 prefetcher: the weight slices this CTA streams in layer l + 1
+    // are requested while layer l computes (the forward touches GBs between two uses of a block's weights: L2 is cold)
+    auto cb = [&]() {
       cluster_arrive_release();
       cluster_wait_acquire();
+    };
+    auto prefetch_layer = [&](int l) {
+      if (elect_one_sync()) {
+        const size_t dd = static_cast<size_t>(d);
+        for (int part = 0; part < 3; ++part)
+          prefetch_l2_bulk(p.wqkv + (static_cast<size_t>(l) * 3 * d + part * d + rank * DC) * dd, static_cast<uint32_t>(DC * d * 2));
+        prefetch_l2_bulk(p.wo + (static_cast<size_t>(l) * d + rank * DC) * dd, static_cast<uint32_t>(DC * d * 2));
+        prefetch_l2_bulk(p.w1 + (static_cast<size_t>(l) * 4 * d + rank * 4 * DC) * dd, static_cast<uint32_t>(4 * DC * d * 2));
+        prefetch_l2_bulk(p.w2 + (static_cast<size_t>(l) * d + rank * DC) * 4 * dd, static_cast<uint32_t>(DC * 4 * d * 2));
+      }
+      __syncwarp();
+    };
+    bool first = true;
+    for (int b = cluster_id; b < p.B; b += n_clusters) {
+      if (first) prefetch_layer(0);
+      cb();
+      for (int l = 0; l < p.layers; ++l) {
+        if (first && l + 1 < p.layers) prefetch_layer(l + 1);     // later images of this cluster find the block's weights in L2
+        cb();
+        cb();
+        cb();
+        cb();
+      }
+      first = false;
     }
   } else {
     // ===================================================== compute warps: thread (t, qd)
@@ -356,7 +402,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
     int cur_l = 0;
     auto mark = [&](int slot) {
       if (p.trace != nullptr && warp == 4 && lane == 0)
-        p.trace[(static_cast<size_t>(blockIdx.x) * p.layers + cur_l) * 16 + slot] = static_cast<unsigned long long>(clock64());
+        p.trace[(static_cast<size_t>(blockIdx.x) * p.layers + cur_l) * 48 + slot] = static_cast<unsigned long long>(clock64());
     };
     auto acc_wait = [&]() {
       mbar_wait(&acc_bar[ev & 3u], (ev >> 2) & 1u);
@@ -404,8 +450,8 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
       float4 gg[NC / 4], bb[NC / 4];
 #pragma unroll
       for (int i = 0; i < NC / 4; ++i) {
-        gg[i] = __ldg(reinterpret_cast<const float4*>(gamma + col0) + i);
-        bb[i] = __ldg(reinterpret_cast<const float4*>(beta + col0) + i);
+        gg[i] = reinterpret_cast<const float4*>(gamma)[i];      // global (first LN of an image) or staged in smem
+        bb[i] = reinterpret_cast<const float4*>(beta)[i];
       }
       named_bar_sync(3, kCompute);
       if (qd == 0) {
@@ -440,7 +486,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
           f[4 * j + 3] = (xv[i + 4 * j + 3] - mean) * rstd * g4.w + b4.w;
         }
         if (dst_f32 == nullptr) {
-          *reinterpret_cast<bf16x8*>(own_chunk_ptr(qd * NC + i)) = pack8(f);
+          st16(own_chunk_ptr(qd * NC + i), f);
         } else {
           *reinterpret_cast<float4*>(dst_f32 + i) = make_float4(f[0], f[1], f[2], f[3]);
           *reinterpret_cast<float4*>(dst_f32 + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -453,7 +499,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
     auto residual_epilogue = [&](const float* bias, int mk) {
       float4 bv[NC / 4];
 #pragma unroll
-      for (int i = 0; i < NC / 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+      for (int i = 0; i < NC / 4; ++i) bv[i] = reinterpret_cast<const float4*>(bias)[i];
       acc_wait();
       mark(mk);
 #pragma unroll
@@ -487,16 +533,32 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
           xv[4 * i + 3] = v.w;
         }
       }
-      ln_step(p.ln1g, p.ln1b, p.eps1, nullptr, 14);
+      ln_step(p.ln1g + col0, p.ln1b + col0, p.eps1, nullptr, 14);
 
       for (int l = 0; l < p.layers; ++l) {
         cur_l = l;
         mark(0);
+        // this layer's biases and LayerNorm parameters (this CTA's columns) -> smem, while the QKV MMAs run:
+        // [0,3DC) bqkv | [3DC,4DC) bo | [4DC,8DC) b1 | [8DC,9DC) b2 | [9DC,11DC) LN2 gamma, beta | [11DC,13DC) next LN gamma, beta
+        for (int i = ctid; i < 13 * DC; i += kCompute) {
+          const int seg = i / DC, m = i - seg * DC;
+          const bool last = l + 1 == p.layers;
+          const float* src;
+          if (seg < 3) src = p.bqkv + l * 3 * d + seg * d + rank * DC + m;
+          else if (seg == 3) src = p.bo + l * d + rank * DC + m;
+          else if (seg < 8) src = p.b1 + l * 4 * d + rank * 4 * DC + (seg - 4) * DC + m;
+          else if (seg == 8) src = p.b2 + l * d + rank * DC + m;
+          else if (seg == 9) src = p.ln2g + l * d + rank * DC + m;
+          else if (seg == 10) src = p.ln2b + l * d + rank * DC + m;
+          else if (seg == 11) src = (last ? p.lnfg : p.ln1g + (l + 1) * d) + rank * DC + m;
+          else src = (last ? p.lnfb : p.ln1b + (l + 1) * d) + rank * DC + m;
+          lpar[i] = __ldg(src);
+        }
+        named_bar_sync(3, kCompute);
         // ---------------- QKV accumulator -> Q / K / V operand tiles (they overwrite the dead LN1(x) operand)
         for (int z = 0; z < p.npass_qkv; ++z) acc_wait();
         mark(1);
         {
-          const float* bq = p.bqkv + l * 3 * d + rank * DC;
 #pragma unroll 1
           for (int z = 0; z < p.npass_qkv; ++z) {
             const int n = p.passes[z].n, g0 = p.passes[z].tcol;    // first q|k|v column of the pass = its TMEM column
@@ -506,8 +568,8 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
               uint32_t v[16];
               tmem_ld16_nowait(tmem_base + lane_addr + static_cast<uint32_t>(g), v);
               const int pt = g / DC, m0 = g - pt * DC;
-              const float4* b4 = reinterpret_cast<const float4*>(bq + pt * d + m0);
-              const float4 bA = __ldg(b4), bB = __ldg(b4 + 1), bC = __ldg(b4 + 2), bD = __ldg(b4 + 3);
+              const float4* b4 = reinterpret_cast<const float4*>(lpar + g);
+              const float4 bA = b4[0], bB = b4[1], bC = b4[2], bD = b4[3];
               tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
@@ -526,7 +588,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
                 const int ci = e / cw, ec = e - ci * cw;
                 // Q(h) | K(h) interleaved per head, then the V tiles
                 uint8_t* tile = pt == 2 ? RA + 2 * TB + head * tile_b : RA + head * 2 * tile_b + pt * tile_b;
-                *reinterpret_cast<bf16x8*>(tile + ci * (kT * rowB) + t * rowB + (((ec >> 3) ^ swz) << 4)) = pack8(f);
+                st16(tile + ci * (kT * rowB) + t * rowB + (((ec >> 3) ^ swz) << 4), f);
               }
             }
           }
@@ -576,7 +638,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
                 f[i] = __bfloat162float(__float2bfloat16_rn(e));
                 sum += f[i];                               // normalise by what the MMA will see
               }
-              *reinterpret_cast<bf16x8*>(prow + ((j ^ (t & 7)) << 4)) = pack8(f);
+              st16(prow + ((j ^ (t & 7)) << 4), f);
             }
             ssum[(grp * 2 + hh) * kT + t] = sum;
           }
@@ -634,14 +696,14 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
         mark(4);
 
         // ---------------- out-proj epilogue + LN2
-        residual_epilogue(p.bo + l * d, 5);
-        ln_step(p.ln2g + l * d, p.ln2b + l * d, p.eps2, nullptr, 7);       // #B
+        residual_epilogue(lpar + 3 * DC + qd * NC, 5);
+        ln_step(lpar + 9 * DC + qd * NC, lpar + 10 * DC + qd * NC, p.eps2, nullptr, 7);       // #B
 
         // ---------------- MLP up: +bias, erf-GELU -> hidden slice
         {
           const int np = p.npass_max;                           // columns per pass
           __nv_bfloat16* hrow = p.hbuf + row * (4 * d) + rank * 4 * DC + qd * (np >> 2);
-          const float* b1 = p.b1 + l * 4 * d + rank * 4 * DC + qd * (np >> 2);
+          const float* b1 = lpar + 4 * DC + qd * (np >> 2);
 #pragma unroll 1
           for (int u = 0; u < p.npass_up; ++u) {
             acc_wait();
@@ -651,7 +713,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
               uint32_t v[16];
               tmem_ld16_nowait(tmem_base + lane_addr + static_cast<uint32_t>(u * np + qd * (np >> 2) + c0), v);
               const float4* b4 = reinterpret_cast<const float4*>(b1 + u * np + c0);
-              const float4 bA = __ldg(b4), bB = __ldg(b4 + 1), bC = __ldg(b4 + 2), bD = __ldg(b4 + 3);
+              const float4 bA = b4[0], bB = b4[1], bC = b4[2], bD = b4[3];
               tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
@@ -665,7 +727,7 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
                 f[5] = gelu_fast(__uint_as_float(v[8 * j + 5]) + bb1.y);
                 f[6] = gelu_fast(__uint_as_float(v[8 * j + 6]) + bb1.z);
                 f[7] = gelu_fast(__uint_as_float(v[8 * j + 7]) + bb1.w);
-                *reinterpret_cast<bf16x8*>(hrow + u * np + c0 + 8 * j) = pack8(f);
+                st16(hrow + u * np + c0 + 8 * j, f);
               }
             }
           }
@@ -677,16 +739,16 @@ cft_gpt_block_kernel(const __grid_constant__ BlockMaps maps, const __grid_consta
         mark(11);
 
         // ---------------- down-proj epilogue + next LN1 / ln_f
-        residual_epilogue(p.b2 + l * d, 12);
+        residual_epilogue(lpar + 8 * DC + qd * NC, 12);
         if (p.dbg != nullptr) {
           float* dp = p.dbg + ((static_cast<size_t>(l) * p.B * kT) + row) * d + col0;
 #pragma unroll
           for (int i = 0; i < NC; ++i) dp[i] = xv[i];
         }
         if (l + 1 < p.layers)
-          ln_step(p.ln1g + (l + 1) * d, p.ln1b + (l + 1) * d, p.eps1, nullptr, 14);            // #E
+          ln_step(lpar + 11 * DC + qd * NC, lpar + 12 * DC + qd * NC, p.eps1, nullptr, 14);    // #E
         else
-          ln_step(p.lnfg, p.lnfb, p.epsf, p.x_out + row * d + col0, 14);                       // #E
+          ln_step(lpar + 11 * DC + qd * NC, lpar + 12 * DC + qd * NC, p.epsf, p.x_out + row * d + col0, 14);   // #E
       }
     }
   }
@@ -740,32 +802,15 @@ struct Plan {
 
 // Cluster size for (B, d): DC = d / C must be 64 or 128, every CTA gets 2 or 4 heads (they are processed in pairs).
 // Prefer the widest split whose B clusters fit on the GPU at once (more SMs per image), else the narrowest.
-bool make_plan(int B, int d, int heads, int forced_c, Plan* pl) {
-  if (heads <= 0 || d % heads) return false;
+bool plan_for(int d, int heads, int C, Plan* pl) {
   const int dk = d / heads;
-  if (dk != 16 && dk != 32 && dk != 64) return false;
-  if (d % 64 || d > 512) return false;
-  int C = 0, narrowest = 0;
-  for (int c = 8; c >= 1; c >>= 1) {
-    if (heads % c || d % c) continue;
-    const int dc = d / c, hpc = heads / c;
-    if ((dc != 64 && dc != 128) || (hpc != 2 && hpc != 4)) continue;
-    if (forced_c) {
-      if (c == forced_c) C = c;
-      continue;
-    }
-    narrowest = c;
-    if (!C && static_cast<long long>(B) * c <= sm_count() - 16) C = c;
-  }
-  if (!C) C = forced_c ? 0 : narrowest;
-  if (!C) return false;
   const int DC = d / C, hpc = heads / C;
   const int TB = kT * DC * 2;
   int ra = kT * d * 2;
   const int tiles = 3 * TB + (dk >= 64 ? 0 : 2 * kT * 256);
   if (tiles > ra) ra = tiles;
   ra = (ra + kAChunk - 1) / kAChunk * kAChunk;
-  const int misc = kMiscFixed + 2 * C * kT * 8;
+  const int misc = kMiscFixed + 2 * C * kT * 8 + 13 * DC * 4;
   const int ring = kSmemMax - 1024 - ra - misc;
   if (ra / kAChunk > kMaxASlots || ring < 3 * 16384) return false;
   pl->C = C;
@@ -781,6 +826,27 @@ bool make_plan(int B, int d, int heads, int forced_c, Plan* pl) {
   pl->smem = 1024 + ra + pl->stages * pl->stage_bytes + misc;
   return true;
 }
+bool make_plan(int B, int d, int heads, int forced_c, Plan* pl) {
+  if (heads <= 0 || d % heads) return false;
+  const int dk = d / heads;
+  if (dk != 16 && dk != 32 && dk != 64) return false;
+  if (d % 64 || d > 512) return false;
+  int cand[4], n = 0;
+  for (int c = 8; c >= 1; c >>= 1) {          // legal splits, widest first
+    if (heads % c || d % c) continue;
+    const int dc = d / c, hpc = heads / c;
+    if ((dc != 64 && dc != 128) || (hpc != 2 && hpc != 4)) continue;
+    if (forced_c && c != forced_c) continue;
+    cand[n++] = c;
+  }
+  // first choice: the widest split whose B clusters are resident at once; then whatever fits, widest first
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < n; ++i) {
+      if (pass == 0 && static_cast<long long>(B) * cand[i] > sm_count() - 16) continue;
+      if (plan_for(d, heads, cand[i], pl)) return true;
+    }
+  return false;
+}
 
 bool g_attr_set = false;
 unsigned long long* g_trace = nullptr;   // cft_debug_block_trace
@@ -795,7 +861,7 @@ cudaError_t launch_block(const cudaLaunchConfig_t& cfg, const BlockMaps& maps, c
 
 using namespace cft;
 
-// Debug timeline: `buf` (device, >= grid * layers * 16 u64) receives clock64 samples of the first compute warp of every CTA
+// Debug timeline: `buf` (device, >= grid * layers * 48 u64) receives clock64 samples of the first compute warp of every CTA
 // for the cft_gpt_block launches that follow; NULL turns it off.  scripts/trace_block.py only.
 extern "C" int cft_debug_block_trace(void* buf) {
   g_trace = static_cast<unsigned long long*>(buf);
@@ -848,6 +914,10 @@ extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
   p.ln1g = a->ln1_g; p.ln1b = a->ln1_b; p.ln2g = a->ln2_g; p.ln2b = a->ln2_b; p.lnfg = a->lnf_g; p.lnfb = a->lnf_b;
   p.x_in = a->x_in; p.x_out = a->x_out;
   p.hbuf = reinterpret_cast<__nv_bfloat16*>(a->workspace);
+  p.wqkv = reinterpret_cast<const __nv_bfloat16*>(a->wqkv);
+  p.wo = reinterpret_cast<const __nv_bfloat16*>(a->wo);
+  p.w1 = reinterpret_cast<const __nv_bfloat16*>(a->w1);
+  p.w2 = reinterpret_cast<const __nv_bfloat16*>(a->w2);
   p.dbg = a->debug_x;
   p.trace = g_trace;
 

@@ -387,8 +387,12 @@ class GPT(nn.Module):
             module.bias.data.zero_()
             module.weight.data.fill_(1.0)
 
-    # one-launch transformer stack (csrc/cft_block.cu); CFT_NO_FUSED_BLOCK=1 / fused_block = False -> 7 launches per layer
+    # one-launch transformer stack (csrc/cft_block.cu); CFT_NO_FUSED_BLOCK=1 / fused_block = False -> 7 launches per layer.
+    # Measured on B200 (profiles/r02_block_*.txt): the cluster-per-image kernel is a per-CTA latency chain -- 1.56x faster
+    # than the per-op path at d = 256 (any batch), equal at d = 512 / batch 32 and slower at d = 512 / small batch, so it
+    # is used up to fused_block_max_d; wider blocks keep the batched GEMM launches.
     fused_block = os.environ.get("CFT_NO_FUSED_BLOCK") is None
+    fused_block_max_d = int(os.environ.get("CFT_FUSED_BLOCK_MAX_D", "256"))
 
     def _weights(self, device):
         srcs = [p for p in self.parameters()]
@@ -438,7 +442,8 @@ class GPT(nn.Module):
         wts = self._weights(rgb.device)
         x = ops.gpt_pool_tokens(rgb, ir, wts["pos"], self.vert_anchors, self.horz_anchors)   # fp32 [B,T,d]
         st = wts["stack"]
-        if self.fused_block and st is not None and st["uniform_eps"] and ops.gpt_block_supported(b, c, self.h, t):
+        if (self.fused_block and c <= self.fused_block_max_d and st is not None and st["uniform_eps"]
+                and ops.gpt_block_supported(b, c, self.h, t)):
             # all layers + ln_f in ONE launch: a cluster of CTAs per image keeps the token tile on chip (csrc/cft_block.cu)
             return ops.gpt_block(x, st, self.h)
         x2d = x.view(b * t, c)

@@ -5,4 +5,6 @@ if [ -z "$SKIP_TESTS" ]; then timeout 600 python -m pytest tests/test_block_gpu.
 timeout 300 python scripts/time_block.py --dims 256 512 2>&1 | tee gpurun_out/block_time.jsonl
 timeout 120 python scripts/trace_block.py --d 256 2>&1 | tee gpurun_out/block_trace_256.txt
 timeout 120 python scripts/trace_block.py --d 512 2>&1 | tee gpurun_out/block_trace_512.txt
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:cft_gpt_block -s 3 -c 1 -o gpurun_out/block256 python scripts/trace_block.py --d 256 > gpurun_out/ncu_block.log 2>&1
+
+timeout 120 python scripts/trace_block.py --d 512 --batch 4 2>&1 | tee gpurun_out/block_trace_512_b4.txt
+timeout 120 python scripts/time_block.py --dims 256 512 --batch 4 2>&1 | tee gpurun_out/block_time_b4.jsonl

@@ -19,12 +19,12 @@ lib = cft._lib.lib()
 for _ in range(3):
     cft.ops.gpt_block(tok, w, g.h, cluster=args.cluster)
 torch.cuda.synchronize()
-buf = torch.zeros(1024 * L * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(1024 * L * 48, dtype=torch.int64, device=dev)
 lib.cft_debug_block_trace(buf.data_ptr())
 cft.ops.gpt_block(tok, w, g.h, cluster=args.cluster)
 torch.cuda.synchronize()
 lib.cft_debug_block_trace(None)
-t = buf.view(1024, L, 16).cpu()
+t = buf.view(1024, L, 48).cpu()
 used = (t[:, 1, 0] != 0).nonzero().flatten()
 t = t[used].double()
 names = ["layer start", "QKV acc ready", "QKV drained->tiles", "attention done", "#A passed", "out acc ready",
@@ -39,3 +39,10 @@ for s in range(1, 16):
     print(f"  {names[s]:28s} {dt.mean():9.0f}  (min {dt.min():7.0f} max {dt.max():7.0f})")
     prev = lay[:, :, s]
 print(f"  layer total {tot:.0f} cycles; whole kernel per CTA {(t[:, L-1, 15] - t[:, 0, 0]).mean():.0f}")
+print("MMA issuer, per GEMM pass (cycles relative to the compute warp's layer start): start | first operands landed | last MMA issued")
+for i in range(10):
+    a = lay[:, :, 16 + 3 * i: 19 + 3 * i]
+    if (a == 0).all():
+        break
+    rel = a - lay[:, :, 0:1]
+    print(f"  pass {i}: {rel[:, :, 0].mean():9.0f} {rel[:, :, 1].mean():9.0f} {rel[:, :, 2].mean():9.0f}   issue span {(a[:, :, 2] - a[:, :, 1]).mean():7.0f}")

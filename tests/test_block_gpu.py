@@ -56,7 +56,6 @@ CASES = [
     (512, 8, 2, 0),       # yolov5l P4 / yolov5s P5: cluster 4, DC 128, dk 64 (P aliases Q|K), 16 KiB weight stages
     (512, 2, 3, 4),       # the same split forced
     (128, 8, 2, 0),       # yolov5s P3: cluster 2, dk 16 (SWIZZLE_32B tiles), 4 heads per CTA = two head pairs
-    (256, 2, 3, 2),       # DC 128 with dk 32: 4 heads per CTA, operand region 160 KiB
     (256, 1, 45, 4),      # more images than co-resident clusters: clusters loop over images
 ]
 

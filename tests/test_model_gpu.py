@@ -179,7 +179,7 @@ def test_forward_engine_graph_pipeline(cft, oracle):
     g = torch.Generator().manual_seed(3)
     batches = [torch.randint(0, 256, (2, 6, 96, 128), dtype=torch.uint8, generator=g).pin_memory() for _ in range(5)]
     eng = cft.ForwardEngine(model, 2, 96, 128, device=DEV, slots=2)
-    assert eng.launches_per_forward > 100
+    assert eng.launches_per_forward > 60
     outs = []
     for i, hb in enumerate(batches):
         if len(eng._pending) == eng.slots:
