@@ -10,8 +10,10 @@ gloo in the CPU tests): parameters are packed, last layer first (the order backw
 bucket is reduced with one asynchronous all-reduce on a side stream as soon as it is filled, so the reduction of the head's
 gradients overlaps whatever still computes; ``finish()`` waits, averages and scatters the result back into ``p.grad``.
 
-Status: host logic + collective only.  The backward kernels that would produce the gradients on this path are not built
- -- ``scripts/allreduce_row.py`` times the exchange for the model's real parameter set.
+Status: the exchange of BASELINE config 4.  ``scripts/train_step.py`` drives it under a train step whose backward is PyTorch
+autograd over the reference's modules (own backward kernels are not built) and times step / all-reduce /
+overlap against ``DistributedDataParallel`` on the same box; ``tests/test_allreduce_gpu.py`` checks it against a plain
+synchronous all-reduce over NCCL.
 """
 from __future__ import annotations
 
@@ -85,14 +87,16 @@ class GradientAllReduce:
 
     def finish(self) -> None:
         """Wait for the reductions, divide by the world size (DDP semantics) and write the result back to ``p.grad``."""
-        for w in self._work:
-            w.wait()
-        self._work = []
         world = self._world()
         dev = self.params[0].device
         cuda = dev.type == "cuda"
         ctx = torch.cuda.stream(self._stream) if cuda else _Null()
         with ctx:
+            # Work.wait() on NCCL orders the CURRENT stream after the collective: call it with the side stream current,
+            # the stream the division and the scatter below run on (gloo's wait() simply blocks the host)
+            for w in self._work:
+                w.wait()
+            self._work = []
             for bucket, flat in zip(self.buckets, self._flat):
                 if flat is None:
                     raise RuntimeError("GradientAllReduce.finish() without start()")

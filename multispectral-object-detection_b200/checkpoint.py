@@ -95,9 +95,8 @@ def from_reference_model(ref_model: nn.Module) -> "_model.Model":
     out.names = list(getattr(ref_model, "names", [str(i) for i in range(getattr(det, "nc", 0))]))
     if isinstance(det, M.Detect):
         out.stride = det.stride
-    for mod in out.modules():                               # utils/torch_utils.py:144-153 (what Model.__init__ sets)
-        if type(mod) is nn.BatchNorm2d:
-            mod.eps, mod.momentum = 1e-3, 0.03
+    # BatchNorm eps / momentum (utils/torch_utils.py:144-153 sets 1e-3 / 0.03 in Model.__init__) travel with the pickled
+    # modules and are copied by _convert_module
     out._plan = _model._plan_graph(out.model)
     return out
 

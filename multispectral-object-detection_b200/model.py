@@ -431,6 +431,10 @@ def _convert_module(m: nn.Module) -> nn.Module:
         if not hasattr(m, "bn"):
             new.conv = nn.Conv2d(c.in_channels, c.out_channels, c.kernel_size, c.stride, c.padding, groups=c.groups, bias=True)
             delattr(new, "bn")
+        else:
+            # load_state_dict copies weights and running statistics only: the fold needs the source's eps as well
+            # (initialize_weights sets 1e-3, utils/torch_utils.py:144-153; nn.BatchNorm2d's default is 1e-5)
+            new.bn.eps, new.bn.momentum = m.bn.eps, m.bn.momentum
     elif name == "Focus":
         c = m.conv.conv
         new = M.Focus(c.in_channels // 4, c.out_channels, c.kernel_size[0], c.stride[0], c.padding[0], c.groups)

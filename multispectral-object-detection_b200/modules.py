@@ -197,7 +197,8 @@ class C3(nn.Module):
     def forward(self, x, out=None):
         x = ops.to_nhwc_bf16(x)
         self.cv1._check(), self.cv2._check()
-        c_ = self.cv1.conv.out_channels
+        _require_eval_bn(getattr(self.cv1, "bn", None)), _require_eval_bn(getattr(self.cv2, "bn", None))   # also when the
+        c_ = self.cv1.conv.out_channels                                    # packed cv1|cv2 weights are already cached
         w12, b12 = self._cv12(x.device)
         cat = ops.conv2d(x, w12, b12, 1, 1, ACT_SILU, cout=2 * c_)        # [cv1(x) | cv2(x)]
         a = cat[:, :c_]

@@ -161,3 +161,42 @@ def test_training_mode_batchnorm_fails_loudly(cft):
     c3 = cft.C3(16, 16, 1)
     with pytest.raises(cft.CftError, match="training mode"):
         c3._cv12("cpu")
+
+
+def test_convert_keeps_batchnorm_eps_numeric(cft):
+    """``convert()`` must fold BatchNorm with the SOURCE module's eps (the reference sets 1e-3,
+    utils/torch_utils.py:144-153; a fresh nn.BatchNorm2d has 1e-5) -- checked on the folded weights of an unfused Conv with
+    small running variances, where the two eps values differ by up to 40 %."""
+    from importlib import import_module
+    M = import_module("multispectral-object-detection_b200.modules")
+    model_mod = import_module("multispectral-object-detection_b200.model")
+    torch.manual_seed(0)
+    src = M.Conv(16, 32, 3, 1).eval()
+    src.bn.eps, src.bn.momentum = 1e-3, 0.03
+    with torch.no_grad():
+        src.bn.running_var.uniform_(1e-4, 2e-3)
+        src.bn.running_mean.normal_(0, 0.1)
+        src.bn.weight.uniform_(0.5, 1.5)
+        src.bn.bias.normal_(0, 0.1)
+    new = model_mod._convert_module(src)
+    assert new.bn.eps == 1e-3 and new.bn.momentum == 0.03 and not new.training
+    w, b = new.folded(torch.device("cpu"))
+    scale = src.bn.weight / torch.sqrt(src.bn.running_var + 1e-3)            # utils/torch_utils.py:181-201
+    w_ref = (src.conv.weight * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(32, 9, 16)
+    b_ref = src.bn.bias - src.bn.running_mean * scale
+    assert torch.allclose(w.float(), w_ref.detach().to(torch.bfloat16).float(), atol=0, rtol=0)
+    assert torch.allclose(b, b_ref.detach(), atol=1e-6)
+    wrong = src.bn.weight / torch.sqrt(src.bn.running_var + 1e-5)
+    assert float((wrong / scale).max()) > 1.2                                # the test can tell the two eps apart
+
+
+def test_c3_and_gpt_refuse_training_mode(cft):
+    """Eval-only forward: a C3 whose cv1|cv2 weights are already packed, and a GPT with dropout, fail loudly in train mode."""
+    from importlib import import_module
+    M = import_module("multispectral-object-detection_b200.modules")
+    c3 = M.C3(32, 32, 1).train()
+    with pytest.raises(cft.CftError):
+        M._require_eval_bn(c3.cv1.bn)
+    g = M.GPT(64, n_layer=1).train()
+    with pytest.raises(cft.CftError):
+        g.tokens(torch.zeros(1, 64, 8, 8), torch.zeros(1, 64, 8, 8))
