@@ -13,9 +13,9 @@ Prints ONE JSON line on rank 0:
   e2e        the same metric through the public API from HOST buffers: every step copies the loader's
              uint8 [B,6,H,W] wire-format batch from pinned host memory to the device and reads the decoded
              detections z back to the host, all inside the timed region
-  roofline   the dominant kernel (tcgen05 implicit-GEMM conv/linear): algorithmic conv+linear FLOPs per
-             step / time spent in that kernel per step (CUDA events around every launch, measured live in a
-             separate profiled pass), against the measured sustained bf16 peak (MEASURED_PEAKS.json)
+  roofline   the dominant kernel (tcgen05 implicit-GEMM conv/linear): the algorithmic FLOPs that kernel executes per
+             step / time it is resident per step -- the union of the in-kernel %globaltimer spans of its launches
+             inside a CUDA-graph replay (the timed mode), measured live -- against the measured sustained bf16 peak
   cpu_baseline  the CPU oracle (a port of the reference's PyTorch forward) timed on the host cores on a
              bounded sample (batch-1 forwards of the same graph/size)
 --impl reference: the reference's own CPU implementation of the path (the oracle port; the reference is
@@ -299,45 +299,115 @@ def extra_rooflines(pkg, model, B, peaks, dev):
     return out
 
 
+def conv_kernel_busy_ms(pkg, model, x_rgb, x_ir, dev, reps=5):
+    """Time the dominant kernel occupies the GPU inside ONE step of the TIMED mode (CUDA-graph replay, RGB / IR branches on
+    two streams, programmatic dependent launch): every cft_conv2d launch of a freshly captured graph reports
+    {first CTA start, last CTA end} in %globaltimer ns (cft_debug_conv_spans); the union of those intervals is the time at
+    least one launch of the kernel is resident, <= the step time by construction.  Returns (union ms, sum of spans ms,
+    launches, graph replay ms), medians over `reps` replays."""
+    import ctypes
+    import torch
+    lib = pkg._lib.lib()
+    MAXL = 1024
+    buf = torch.zeros(2 * MAXL, dtype=torch.int64, device=dev)
+    init = torch.zeros(2 * MAXL, dtype=torch.int64)
+    init[0::2] = torch.iinfo(torch.int64).max
+    init = init.to(dev)
+    stream = torch.cuda.Stream(dev)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    pkg._lib.check(lib.cft_debug_conv_spans(ctypes.c_void_p(buf.data_ptr()), MAXL), "cft_debug_conv_spans")
+    try:
+        with torch.no_grad(), torch.cuda.graph(g, stream=stream):
+            model(x_rgb, x_ir)
+    finally:
+        pkg._lib.check(lib.cft_debug_conv_spans(ctypes.c_void_p(0), 0), "cft_debug_conv_spans")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    unions, sums, replays, n = [], [], [], 0
+    for _ in range(reps + 1):
+        buf.copy_(init)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            g.replay()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        t = buf.cpu().view(-1, 2)
+        t = t[t[:, 1] > 0]
+        n = int(t.shape[0])
+        iv = sorted(zip(t[:, 0].tolist(), t[:, 1].tolist()))
+        busy, cs, ce = 0, iv[0][0], iv[0][1]
+        for a, b in iv[1:]:
+            if a > ce:
+                busy += ce - cs
+                cs, ce = a, b
+            else:
+                ce = max(ce, b)
+        busy += ce - cs
+        unions.append(busy / 1e6)
+        sums.append(float((t[:, 1] - t[:, 0]).sum()) / 1e6)
+        replays.append(e0.elapsed_time(e1))
+    med = lambda v: sorted(v[1:])[len(v[1:]) // 2]          # the first replay of a fresh graph is a warm-up
+    del g
+    return med(unions), med(sums), n, med(replays)
+
+
 def gpu_eager_baseline(pkg, cfg, B, dev, steps=5):
-    """The existing GPU path on the same device: the reference's op sequence as PyTorch eager ops (cuDNN / cuBLAS through
-    torch.nn.functional -- the oracle's restatement with its tensors on the GPU), BN fused, bf16, channels_last: what
-    `test.py --half` / `detect_twostream.py` run.  A reported baseline beside cpu_baseline; never on the product path."""
+    """The existing GPU path on the same device, a reported baseline beside cpu_baseline (never on the product path):
+    the UNMODIFIED reference's own modules in PyTorch eager (cuDNN / cuBLAS), `attempt_load`-style fused and `.half()` as
+    test.py:66-68,107 / detect_twostream.py:40-41,72 run them -- when the reference tree (or its staged copy
+    baseline/_ref, oracle/stage_reference.py) is present; else the oracle's restatement of the same op sequence with its
+    tensors on the GPU (bf16, channels_last)."""
     import torch
     from oracle import cft_oracle as O
-    sd = {}
-    for k, v in fused_state(O.init_state(cfg, seed=0), O.BN_EPS).items():
-        if v.is_floating_point():
-            v = v.to(dev, torch.bfloat16)
-            if v.dim() == 4:
-                v = v.contiguous(memory_format=torch.channels_last)
-        else:
-            v = v.to(dev)
-        sd[k] = v
+    from oracle import ref_shim
     g = torch.Generator().manual_seed(1)
-    x = torch.rand(B, 3, H, W, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    x2 = torch.rand(B, 3, H, W, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    for _ in range(2):
-        O.forward(sd, cfg, x, x2)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        O.forward(sd, cfg, x, x2)
-    e1.record()
-    torch.cuda.synchronize()
+    x = torch.rand(B, 3, H, W, generator=g)
+    x2 = torch.rand(B, 3, H, W, generator=g)
+    if ref_shim.available():
+        yt = ref_shim.import_reference()
+        rm = yt.Model(ref_shim.reference_yaml(CFG_NAME), ch=3)
+        rm.load_state_dict(O.init_state(cfg, seed=0), strict=True)
+        rm = rm.float().fuse().eval().to(dev).half()
+        x, x2 = x.to(dev).half(), x2.to(dev).half()
+        fwd = lambda: rm(x, x2)
+        kind = "the reference's own modules, PyTorch eager (cuDNN/cuBLAS), fused, .half() as test.py:66-68, same GPU"
+    else:
+        sd = {}
+        for k, v in fused_state(O.init_state(cfg, seed=0), O.BN_EPS).items():
+            if v.is_floating_point():
+                v = v.to(dev, torch.bfloat16)
+                if v.dim() == 4:
+                    v = v.contiguous(memory_format=torch.channels_last)
+            else:
+                v = v.to(dev)
+            sd[k] = v
+        x = x.to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x2 = x2.to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        fwd = lambda: O.forward(sd, cfg, x, x2)
+        kind = "pytorch eager (cuDNN/cuBLAS) restatement of the reference op sequence, BN fused, bf16 channels_last, same GPU"
+    with torch.no_grad():
+        for _ in range(2):
+            fwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fwd()
+        e1.record()
+        torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    del sd, x, x2
+    del fwd, x, x2
     torch.cuda.empty_cache()
-    return {"value": B / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "kind": "pytorch eager (cuDNN/cuBLAS), BN fused, "
-            "bf16 channels_last, same GPU", "sample": f"{steps} forwards of batch {B} @ {H}x{W}"}
+    return {"value": B / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "kind": kind,
+            "sample": f"{steps} forwards of batch {B} @ {H}x{W}"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -476,8 +546,8 @@ def main():
         peaks = load_peaks()
         flops_pair = O.conv_linear_flops(cfg, H, W)
         attn_core = sum(8 * 4.0 * 128 * 128 * d for d in (256, 512, 1024))
-        # per-launch CUDA events only add up when launches are serialised: the profiled pass walks the graph on ONE
-        # stream (the timed region overlaps the RGB and IR branches on two)
+        # (1) per-kernel totals of one step: per-launch CUDA events only add up when launches are serialised, so this pass
+        # walks the graph eagerly on ONE stream -- it feeds `kernel_ms_per_step` (shares), not the roofline
         two = model.two_streams
         model.two_streams = False
         pkg._lib.prof_enable(True)
@@ -490,9 +560,21 @@ def main():
         pkg._lib.prof_enable(False)
         model.two_streams = two
         kernel_ms = {k: round(v[0] / nprof, 4) for k, v in prof.items() if v[1]}
-        conv_ms, conv_n = prof["conv_tcgen05"]
-        conv_flops_step = (flops_pair - attn_core) * B
-        achieved = conv_flops_step * nprof / (conv_ms / 1e3) / 1e12
+        # (2) the roofline of the dominant kernel, measured in the TIMED mode: in-kernel %globaltimer spans of every conv /
+        # linear launch inside a CUDA-graph replay (two streams, PDL) -> time the kernel is resident per step
+        busy_ms, span_sum_ms, conv_n, replay_ms = conv_kernel_busy_ms(pkg, model, x_rgb, x_ir, dev)
+        # FLOPs that kernel executes: conv + linear FLOPs of the graph minus what other kernels run:
+        # the attention cores, the fused uint8 Focus layers (cft_focus_tcgen05_kernel) and the Linear layers of the CFT
+        # blocks that run inside the one-launch cft_gpt_block kernel
+        c0 = model.model[0].conv.conv.out_channels
+        focus_flops = 2 * 2.0 * (H // 2) * (W // 2) * c0 * 12 * 9
+        blk_flops = 0.0
+        for m_ in model.model:
+            if isinstance(m_, pkg.GPT) and m_.fused_block and m_.n_embd <= m_.fused_block_max_d \
+                    and pkg.ops.gpt_block_supported(B, m_.n_embd, m_.h, 2 * m_.vert_anchors * m_.horz_anchors):
+                blk_flops += 24576.0 * m_.n_embd * m_.n_embd
+        conv_flops_step = (flops_pair - attn_core - focus_flops - blk_flops) * B
+        achieved = conv_flops_step / (busy_ms / 1e3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
         if os.path.isfile(tpath):          # summed dram__bytes_{read,write} of the kernel's launches in one step (ncu)
@@ -500,9 +582,14 @@ def main():
         roofline = {"kernel": "cft_conv_tcgen05_kernel", "bound": "tensor", "achieved": achieved,
                     "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                     "peak_source": peaks["source"] + " sustained bf16", "traffic": traffic,
-                    "traffic_note": "sum over the kernel's launches of one step (profiles/r01_conv_dram_traffic.json)",
-                    "launches_per_step": conv_n // nprof, "ms_per_step_in_kernel": conv_ms / nprof,
+                    "traffic_note": "sum over the kernel's launches of one step (profiles/r01_conv_dram_traffic.json, ncu)",
+                    "launches_per_step": conv_n, "ms_per_step_in_kernel": busy_ms,
+                    "how": "union of the [first CTA start, last CTA end] %globaltimer spans of the kernel's launches inside "
+                           "one CUDA-graph replay of the step (the timed mode: two streams, PDL); "
+                           f"sum of spans {span_sum_ms:.3f} ms, replay {replay_ms:.3f} ms",
                     "algorithmic_gflop_per_step": conv_flops_step / 1e9,
+                    "gflop_per_step_in_other_kernels": {"attention_core": attn_core * B / 1e9, "focus_fused": focus_flops * B / 1e9,
+                                                        "cft_gpt_block": blk_flops * B / 1e9},
                     "whole_forward_tensor_frac": (flops_pair * value / world) / (peaks["tflops_sustained"] * 1e12)}
 
     extras = None
@@ -530,6 +617,8 @@ def main():
         dist.barrier()
     if rank == 0:
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()      # rank 0 at N = 1 only
+        if cpu is not None and eager is not None:
+            cpu["gpu_eager_same_box"] = eager      # the existing GPU path (PyTorch eager, cuDNN / cuBLAS) beside the CPU number
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -153,6 +153,7 @@ class Model(nn.Module):
         the tail wave of the RGB chain's kernels (and vice versa).  Fork/join uses CUDA events only, so the walk is
         capturable into a CUDA graph."""
         plan = self._plan
+        cap = getattr(self, "_capture", None)              # dict: layer index -> output, filled when set (tests)
         y: List = []
         concat_bufs: Dict[int, torch.Tensor] = {}
         fused: Dict[int, torch.Tensor] = {}
@@ -201,6 +202,8 @@ class Model(nn.Module):
                     x = m(x)
             if chains and not on_side and i in wanted_src and i not in src_events:
                 src_events[i] = main.record_event()
+            if cap is not None:                                # debug / tests: every layer's output (None for a fused GPT)
+                cap[i] = x
             y.append(x if i in self.save else None)
         if side_active:                                        # graph without a closing GPT (not the x3 layout)
             main.wait_stream(side)

@@ -2,15 +2,18 @@
 
 The reference's ``models/common.py:16-18`` imports matplotlib/seaborn through
 ``utils.plots``/``utils.metrics``; neither is installed.  Four empty ``sys.modules`` stubs
-make it importable.  Nothing under ``/root/reference`` is modified or copied.
-The GPU box has no ``/root/reference``: only ``oracle/make_golden.py`` and the ``-m "not gpu"``
-cross-check tests (which skip when the tree is absent) use this shim.
+make it importable.  Nothing under ``/root/reference`` is modified.
+The GPU box has no ``/root/reference``: there the shim falls back to ``baseline/_ref/`` -- a git-ignored copy of the
+tree's ``models/`` and ``utils/`` staged by ``oracle/stage_reference.py`` at build time -- so that the
+reference-through-the-boundary tests run on the GPU as well; they skip when neither exists.
 """
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("CFT_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REF_ROOT = os.environ.get("CFT_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/models/yolo_test.py") else _STAGED)
 
 
 def available() -> bool:
