@@ -48,6 +48,31 @@ class GradientAllReduce:
         self._flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
         self._work: List = []
         self._stream = None
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._ready = [0] * len(self.buckets)
+        self._hooks: List = []
+
+    # ------------------------------------------------------------------ overlap with backward
+    def attach(self) -> "GradientAllReduce":
+        """Launch every bucket's all-reduce from inside ``backward`` as soon as the last gradient of the bucket has been
+        accumulated (``register_post_accumulate_grad_hook``) -- what DDP's reducer does (train.py:654-658) -- instead of after
+        the whole backward.  Call ``finish()`` after ``backward``; ``detach()`` removes the hooks."""
+        if self._hooks:
+            return self
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        return self
+
+    def detach(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    def _on_grad(self, p) -> None:
+        i = self._bucket_of[id(p)]
+        self._ready[i] += 1
+        if self._ready[i] == len(self.buckets[i]) and self._flat[i] is None:
+            self._launch(i)
 
     # ------------------------------------------------------------------ sizes
     @property
@@ -61,32 +86,39 @@ class GradientAllReduce:
     def _world(self) -> int:
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def start(self) -> None:
-        """Pack every bucket and launch its all-reduce (asynchronously; on CUDA on a side stream that waits for the
-        gradients' producer stream)."""
-        if self._work:
-            raise RuntimeError("GradientAllReduce.start(): previous exchange not finished")
+    def _launch(self, i: int) -> None:
+        bucket = self.buckets[i]
         dev = self.params[0].device
         cuda = dev.type == "cuda"
         if cuda and self._stream is None:
             self._stream = torch.cuda.Stream(dev)
         if cuda:
-            self._stream.wait_stream(torch.cuda.current_stream(dev))
-        for i, bucket in enumerate(self.buckets):
-            for p in bucket:
-                if p.grad is None:
-                    raise RuntimeError("GradientAllReduce: a parameter has no gradient (unused parameters are not "
-                                       "supported, as with DDP's default find_unused_parameters=False)")
-            ctx = torch.cuda.stream(self._stream) if cuda else _Null()
-            with ctx:
-                wire = self.dtype or bucket[0].grad.dtype
-                flat = torch.cat([p.grad.reshape(-1).to(wire) for p in bucket])
-                self._flat[i] = flat
-                if self._world() > 1:
-                    self._work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._stream.wait_stream(torch.cuda.current_stream(dev))     # the gradients' producer stream
+        for p in bucket:
+            if p.grad is None:
+                raise RuntimeError("GradientAllReduce: a parameter has no gradient (unused parameters are not "
+                                   "supported, as with DDP's default find_unused_parameters=False)")
+        ctx = torch.cuda.stream(self._stream) if cuda else _Null()
+        with ctx:
+            wire = self.dtype or bucket[0].grad.dtype
+            flat = torch.cat([p.grad.reshape(-1).to(wire) for p in bucket])
+            self._flat[i] = flat
+            if self._world() > 1:
+                self._work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def start(self) -> None:
+        """Pack every bucket that has not been launched by a hook yet and launch its all-reduce (asynchronously; on CUDA on
+        a side stream that waits for the gradients' producer stream)."""
+        if self._work and not self._hooks:
+            raise RuntimeError("GradientAllReduce.start(): previous exchange not finished")
+        for i in range(len(self.buckets)):
+            if self._flat[i] is None:
+                self._launch(i)
 
     def finish(self) -> None:
         """Wait for the reductions, divide by the world size (DDP semantics) and write the result back to ``p.grad``."""
+        if any(f is None for f in self._flat):
+            self.start()                    # hook mode: buckets whose parameters got no gradient hook this step
         world = self._world()
         dev = self.params[0].device
         cuda = dev.type == "cuda"
@@ -110,6 +142,7 @@ class GradientAllReduce:
         if cuda:
             torch.cuda.current_stream(dev).wait_stream(self._stream)
         self._flat = [None] * len(self.buckets)
+        self._ready = [0] * len(self.buckets)
 
     def reduce(self) -> None:
         self.start()

@@ -74,3 +74,52 @@ def test_gradient_allreduce_single_process_is_identity():
     assert len(red.buckets) == 2 and red.buckets[0][0] is lin.bias          # last parameter first
     red.reduce()
     assert all(bool((p.grad == 3).all()) for p in lin.parameters())
+
+
+def _hook_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    ar = importlib.import_module("multispectral-object-detection_b200.allreduce")
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(),
+                              torch.nn.Linear(32, 4))
+    params = list(net.parameters())
+    red = ar.GradientAllReduce(params, bucket_bytes=2048).attach()           # several buckets, launched from backward
+    xs = [torch.randn(8, 16, generator=torch.Generator().manual_seed(7 + r)) for r in range(world)]
+    grads = []
+    for r in range(world):                                                   # what each rank computes on its own
+        net.zero_grad()
+        red.detach()
+        net(xs[r]).square().mean().backward()
+        grads.append([p.grad.clone() for p in params])
+    expect = [sum(g[i] for g in grads) / world for i in range(len(params))]
+    errs = []
+    for step in range(2):                                                    # two steps: the per-step state resets
+        net.zero_grad()
+        red.attach()
+        net(xs[rank]).square().mean().backward()
+        launched_in_backward = sum(f is not None for f in red._flat)
+        red.finish()
+        errs.append(max(float((p.grad - e).abs().max()) for p, e in zip(params, expect)))
+    dist.destroy_process_group()
+    q.put((rank, errs, launched_in_backward, len(red.buckets)))
+
+
+def test_gradient_allreduce_hooks_launch_buckets_during_backward():
+    """attach(): every bucket's all-reduce is launched by the post-accumulate-grad hook of its last parameter (the overlap
+    DDP's reducer provides, train.py:654-658); the averaged gradients equal the plain mean."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hook_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs, launched, nb in res:
+        assert max(errs) <= 1e-6, (rank, errs)
+        assert nb >= 3 and launched == nb
