@@ -410,6 +410,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default=CFG_NAME, help="graph (config name); the default is BASELINE.json's headline config 2; "
+                    "yolov5x_fusion_transformerx3_FLIR_aligned = config 5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--slots", type=int, default=2, help="engine slots (double-buffered copy pipeline)")
@@ -441,7 +443,7 @@ def main():
     K = args.steps
     B = args.batch
 
-    cfg = pkg.named_config(CFG_NAME)
+    cfg = pkg.named_config(args.cfg)
     torch.manual_seed(0)
     model = pkg.Model(cfg).eval()
     # random-init weights of the architecture with non-degenerate BN statistics / pos_emb
@@ -545,7 +547,7 @@ def main():
         from oracle import cft_oracle as O       # FLOP model only -- nothing is executed
         peaks = load_peaks()
         flops_pair = O.conv_linear_flops(cfg, H, W)
-        attn_core = sum(8 * 4.0 * 128 * 128 * d for d in (256, 512, 1024))
+        attn_core = sum(len(m_.trans_blocks) * 4.0 * 128 * 128 * m_.n_embd for m_ in model.model if isinstance(m_, pkg.GPT))
         # (1) per-kernel totals of one step: per-launch CUDA events only add up when launches are serialised, so this pass
         # walks the graph eagerly on ONE stream -- it feeds `kernel_ms_per_step` (shares), not the roofline
         two = model.two_streams
@@ -593,14 +595,14 @@ def main():
                     "whole_forward_tensor_frac": (flops_pair * value / world) / (peaks["tflops_sustained"] * 1e12)}
 
     extras = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and not args.no_extras and args.cfg == CFG_NAME:
         try:
             extras = extra_rooflines(pkg, model, B, load_peaks(), dev)
         except Exception as e:          # never lose the headline line over a side measurement
             extras = {"error": repr(e)[:300]}
 
     eager = None
-    if rank == 0 and world == 1 and not args.no_eager_baseline:
+    if rank == 0 and world == 1 and not args.no_eager_baseline and args.cfg == CFG_NAME:
         try:
             eager = gpu_eager_baseline(pkg, cfg, B, dev)
         except Exception as e:          # a side measurement must never cost the headline line
@@ -616,14 +618,14 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline()      # rank 0 at N = 1 only
+        cpu = None if (args.no_cpu_baseline or world > 1 or args.cfg != CFG_NAME) else cpu_baseline()      # rank 0 at N = 1 only
         if cpu is not None and eager is not None:
             cpu["gpu_eager_same_box"] = eager      # the existing GPU path (PyTorch eager, cuDNN / cuBLAS) beside the CPU number
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{CFG_NAME} forward (eval, BN folded), batch {B} per GPU @ {H}x{W}, nc=3",
+            "config": {"workload": f"{args.cfg} forward (eval, BN folded), batch {B} per GPU @ {H}x{W}, nc={cfg['nc']}",
                        "global_batch": B * world, "parallelism": f"dp{world} (pairs sharded, no data-path collective)",
                        "l2": "working set (inputs 79 MB + weights 412 MB + activations > 5 GB per step) >> 126 MB L2",
                        "launch": "cuda-graph replay" if graph is not None else "eager",
