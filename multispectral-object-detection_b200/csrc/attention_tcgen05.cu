@@ -7,7 +7,9 @@
 //   O = P V        tcgen05.mma  128 x dk x 128   (B = V as loaded: [key][dk] = MN-major operand)
 //   out = O / rowsum  -> bf16, heads merged ([B*128, C])
 //
-// The head dim is cut into chunks of 64 / 32 / 16 elements (widest first: 128 = 64+64, 80 = 64+16, 160 = 64+64+32);
+// The head dim is cut into chunks of 64 / 32 / 16 elements (widest first: 128 = 64+64, 80 = 64+16, 160 = 64+64+32,
+// 40 = 32+16 with the last 8 columns zero-filled by TMA: the tensor maps are 3-D (head dim, q|k|v x head, token), so a box
+// that overhangs the head dim reads zeros, not the next head);
 // every chunk is its own [128 x width] tile with the swizzle mode that matches its row length (128B / 64B / 32B),
 // loaded through the tensor map of that width.  QK^T walks the chunks along K; PV issues one MMA group per chunk
 // (N = chunk width) into that chunk's TMEM columns (a uniform 64-wide split is issued as ONE N = dk group).  Replaces models/common.py:497-510 (two batched matmuls + softmax that
@@ -25,6 +27,7 @@ constexpr int kThreads = 128;
 constexpr int kMaxChunks = 4;
 struct AttnParams {
   int C, heads, dk;
+  int dkp;                    // head dim padded to the chunk widths (multiple of 16): smem tiles / TMEM columns
   int nchunk;                 // head-dim chunks
   int cw[kMaxChunks];         // chunk width in elements (64 / 32 / 16)
   int coff[kMaxChunks];       // first head-dim element of the chunk
@@ -46,7 +49,7 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile_bytes = kT * p.dk * 2;              // one of Q / K / V (all chunks)
+  const int tile_bytes = kT * p.dkp * 2;             // one of Q / K / V (all chunks, head dim zero-padded to dkp)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + tile_bytes;
   uint8_t* sV = sK + tile_bytes;
@@ -81,11 +84,10 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
     mbar_arrive_expect_tx(tma_bar, 3u * static_cast<uint32_t>(tile_bytes));
     const int r0 = b * kT;
     for (int c = 0; c < p.nchunk; ++c) {
-      const int col = h * p.dk + p.coff[c];
-      const CUtensorMap* m = &maps.m[p.map[c]];
-      tma_load_2d(sQ + p.soff[c], m, tma_bar, col, r0);
-      tma_load_2d(sK + p.soff[c], m, tma_bar, p.C + col, r0);
-      tma_load_2d(sV + p.soff[c], m, tma_bar, 2 * p.C + col, r0);
+      const CUtensorMap* m = &maps.m[p.map[c]];     // (head-dim element, part * heads + head, token row)
+      tma_load_3d(sQ + p.soff[c], m, tma_bar, p.coff[c], h, r0);
+      tma_load_3d(sK + p.soff[c], m, tma_bar, p.coff[c], p.heads + h, r0);
+      tma_load_3d(sV + p.soff[c], m, tma_bar, p.coff[c], 2 * p.heads + h, r0);
     }
   }
   mbar_wait(tma_bar, 0);
@@ -148,7 +150,7 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
     // single N = dk group whose descriptor steps from chunk to chunk through LBO
     const int groups = p.uniform64 ? 1 : p.nchunk;
     for (int c = 0; c < groups; ++c) {
-      const uint32_t n = p.uniform64 ? static_cast<uint32_t>(p.dk) : static_cast<uint32_t>(p.cw[c]);
+      const uint32_t n = p.uniform64 ? static_cast<uint32_t>(p.dkp) : static_cast<uint32_t>(p.cw[c]);
       const uint32_t row_b = static_cast<uint32_t>(p.cw[c]) * 2u;
       const uint32_t idesc = umma_idesc_ex(128, n, 0, 1);
       const uint32_t sbo_v = 8u * row_b;                        // next 8 keys
@@ -167,7 +169,7 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
   // ---- epilogue: out[b*128 + t][h*dk + c] = O[t][c] / sum ----
   const float inv = 1.0f / sum;
   __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * kT + tid) * p.C + h * p.dk;
-  for (int c0 = 0; c0 < p.dk; c0 += 32) {
+  for (int c0 = 0; c0 < p.dkp; c0 += 32) {
     uint32_t v[32];
     tmem_ld32(tmem_o + lane_addr + c0, v);
 #pragma unroll
@@ -202,7 +204,8 @@ EncodeTiledFn get_encode() {
 bool g_attr = false;
 
 int launch_attention(const AttnMaps& maps, const AttnParams& p, int B, cudaStream_t stream) {
-  const int dk = p.dk, heads = p.heads;
+  const int heads = p.heads;
+  const int dk = p.dkp;
   const int smem = 1024 + 3 * kT * dk * 2 + (dk >= 64 ? 0 : 2 * kT * 128) + 64;
   if (!g_attr) {
     int rc = check_cuda(cudaFuncSetAttribute(cft_attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -222,7 +225,7 @@ namespace cft {
 // Returns CFT_E_UNSUPPORTED when the shape is outside this kernel (caller falls back to the CUDA-core kernel).
 int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads, cudaStream_t stream) {
   const int dk = C / heads;
-  if (T != kT || C % heads || dk % 16 || dk < 16 || dk > 256 || B > 65535) return CFT_E_UNSUPPORTED;
+  if (T != kT || C % heads || dk % 8 || dk < 16 || dk > 256 || B > 65535) return CFT_E_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(qkv) % 16 || (3 * C) % 8) return CFT_E_UNSUPPORTED;
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -237,7 +240,7 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
     bool used[3] = {false, false, false};
     while (off < dk) {
       const int rem = dk - off;
-      const int w = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+      const int w = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);     // the last chunk may overhang (rem = 8): zero-filled
       if (n == kMaxChunks) return CFT_E_UNSUPPORTED;
       p.cw[n] = w;
       p.coff[n] = off;
@@ -250,8 +253,9 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
       ++n;
     }
     p.nchunk = n;
+    p.dkp = off;
     p.uniform64 = (dk % 64 == 0) ? 1 : 0;
-    p.tmem_cols = (128 + dk <= 256) ? 256 : 512;
+    p.tmem_cols = (128 + p.dkp <= 256) ? 256 : 512;
     p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     AttnMaps maps;
@@ -259,13 +263,14 @@ int attention_tcgen05(const void* qkv, void* out, int B, int T, int C, int heads
     for (int i = 0; i < 3; ++i) {
       if (!used[i]) continue;
       const int w = i == 0 ? 64 : (i == 1 ? 32 : 16);
-      cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)B * kT};
-      cuuint64_t str[1] = {(cuuint64_t)(3 * C) * 2};
-      cuuint32_t box[2] = {(cuuint32_t)w, (cuuint32_t)kT};
-      cuuint32_t estr[2] = {1, 1};
+      // qkv [B*128, 3C] viewed as (head-dim element, q|k|v x head, token): a box overhanging dk is zero-filled
+      cuuint64_t dims[3] = {(cuuint64_t)dk, (cuuint64_t)(3 * heads), (cuuint64_t)B * kT};
+      cuuint64_t str[2] = {(cuuint64_t)dk * 2, (cuuint64_t)(3 * C) * 2};
+      cuuint32_t box[3] = {(cuuint32_t)w, 1, (cuuint32_t)kT};
+      cuuint32_t estr[3] = {1, 1, 1};
       const CUtensorMapSwizzle swz = w == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                              : (w == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-      CUresult r = enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, str, box, estr,
+      CUresult r = enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, str, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
