@@ -307,11 +307,12 @@ def test_layernorm(C, cft):
 
 
 @pytest.mark.parametrize("C,heads", [(128, 8), (256, 8), (512, 8), (1024, 8), (320, 8),
-                                     (640, 8), (1280, 8), (384, 8), (896, 8), (1536, 8)])
+                                     (640, 8), (1280, 8), (384, 8), (896, 8), (1536, 8), (192, 8), (576, 8)])
 def test_attention_core(C, heads, cft):
     """softmax(q k^T / sqrt(dk)) v per (image, head), 128 tokens (common.py:497-510).  Head dims 16..128 (yolov5s/l) and
     the mixed-chunk splits of the tcgen05 kernel: 80 = 64+16 and 160 = 64+64+32 (yolov5x P4/P5), 48 = 32+16,
-    112 = 64+32+16, 192 = 3x64; 40 (yolov5x P3) is not a multiple of 16 and takes the CUDA-core kernel."""
+    112 = 64+32+16, 192 = 3x64; 40 (yolov5x P3) = 32 + 16 and 24 / 72 likewise, the overhanging 8 columns zero-filled by the
+    3-D TMA box (head dim, q|k|v x head, token)."""
     B, T = 3, 128
     qkv = rnd(B * T, 3 * C, seed=1).to(DEV).to(torch.bfloat16)
     out = cft.ops.attention(qkv, B, T, C, heads)
