@@ -109,14 +109,28 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// 8 bf16 = one 16-byte memory transaction.  The payload is a uint4 on purpose: a struct of four __nv_bfloat162 is copied
+// member by member (four 4-byte LDG / STG per copy -- measured: every mover of the path issued 4x the memory instructions
+// and, with one row per lane, 4x the L2 sector requests), a uint4 member is one LDG.128 / STG.128.
 struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
+  __device__ __forceinline__ __nv_bfloat162 get(int i) const {
+    const uint32_t w = i == 0 ? u.x : (i == 1 ? u.y : (i == 2 ? u.z : u.w));
+    return *reinterpret_cast<const __nv_bfloat162*>(&w);
+  }
+  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&h);
+    if (i == 0) u.x = w;
+    else if (i == 1) u.y = w;
+    else if (i == 2) u.z = w;
+    else u.w = w;
+  }
 };
 
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
+    float2 t = __bfloat1622float2(p.get(i));
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -124,7 +138,7 @@ __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) p.set(i, __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]));
   return p;
 }
 

@@ -52,10 +52,11 @@ pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb, const __nv
       for (int q = 1; q < slices; ++q)
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += red[(q * nv + cv) * 8 + i];
-      float* o = tok + (static_cast<long long>(b) * T + t) * C + (v0 + cv) * 8;
-      const float* pe = pos + static_cast<long long>(t) * C + (v0 + cv) * 8;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = s[i] * inv + pe[i];
+      float4* o = reinterpret_cast<float4*>(tok + (static_cast<long long>(b) * T + t) * C + (v0 + cv) * 8);
+      const float4* pe = reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * C + (v0 + cv) * 8);
+      const float4 p0 = __ldg(pe), p1 = __ldg(pe + 1);
+      o[0] = make_float4(s[0] * inv + p0.x, s[1] * inv + p0.y, s[2] * inv + p0.z, s[3] * inv + p0.w);
+      o[1] = make_float4(s[4] * inv + p1.x, s[5] * inv + p1.y, s[6] * inv + p1.z, s[7] * inv + p1.w);
     }
     __syncthreads();
   }
@@ -110,9 +111,11 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
       if constexpr (kOutF32) {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * C)[i] = make_float4(o0, o1, o2, o3);
       } else {
-        __nv_bfloat162* yo = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C) + 2 * i;
-        yo[0] = __floats2bfloat162_rn(o0, o1);
-        yo[1] = __floats2bfloat162_rn(o2, o3);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * C)[i] = pk;
       }
     }
   }
@@ -148,9 +151,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     __nv_bfloat162* dv = reinterpret_cast<__nv_bfloat162*>(sv + r * ldp + cv * 8);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      dq[j] = q.v[j];
-      dkk[j] = k.v[j];
-      dv[j] = v.v[j];
+      dq[j] = q.get(j);
+      dkk[j] = k.get(j);
+      dv[j] = v.get(j);
     }
   }
   __syncthreads();

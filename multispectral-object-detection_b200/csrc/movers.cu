@@ -126,7 +126,7 @@ struct __align__(16) bf16x16 {
 __device__ __forceinline__ bf16x8 max8(const bf16x8& a, const bf16x8& b) {
   bf16x8 r;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) r.v[i] = __hmax2(a.v[i], b.v[i]);
+  for (int i = 0; i < 4; ++i) r.set(i, __hmax2(a.get(i), b.get(i)));
   return r;
 }
 __global__ void maxpool_cascade_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y0,

@@ -83,9 +83,32 @@ for i, nm in enumerate(names):
     a = agg.setdefault(nm, [0, 0.0])
     a[0] += 1
     a[1] += float(dur[i])
-print(f"{'shape':44s} {'n':>3s} {'us tot':>8s} {'us each':>8s}")
+import re
+
+
+def ideal_us(nm):
+    """Roofline time of one launch of this shape: max(FLOPs / sustained bf16 peak, compulsory bytes / HBM peak)."""
+    m = re.match(r"conv\s+(\d+)->\s*(\d+) k(\d)s(\d) (\d+)x(\d+)", nm)
+    if m:
+        cin, cout, k, st, h, w = map(int, m.groups())
+        ho, wo = (h + st - 1) // st, (w + st - 1) // st
+        fl = 2.0 * B * ho * wo * cout * cin * k * k
+        by = 2.0 * (B * h * w * cin + B * ho * wo * cout * (2 if "+res" in nm else 1) + cout * cin * k * k)
+    else:
+        m = re.match(r"gemm M(\d+) K\s*(\d+) N\s*(\d+)", nm)
+        mm, kk, nn = map(int, m.groups())
+        fl = 2.0 * mm * kk * nn
+        by = 2.0 * (mm * kk + mm * nn + kk * nn) + (8.0 * mm * nn if "+res" in nm else 0.0)
+    return max(fl / 1385.4e12, by / 6584.8e9) * 1e6, fl, by
+
+
+print(f"{'shape':44s} {'n':>3s} {'us tot':>8s} {'us each':>8s} {'roofline':>9s} {'of roof':>8s} {'lost us':>8s}  (roofline = max(FLOPs / 1385 TF, bytes / 6585 GB/s))")
+tot_lost = 0.0
 for nm, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{nm:44s} {c:3d} {us:8.0f} {us / c:8.1f}")
+    idl, fl, by = ideal_us(nm)
+    tot_lost += us - c * idl
+    print(f"{nm:44s} {c:3d} {us:8.0f} {us / c:8.1f} {idl:9.1f} {100 * c * idl / us:7.0f}% {us - c * idl:8.0f}")
+print(f"sum of (span - roofline) over all launches: {tot_lost:.0f} us")
 if "--list" in sys.argv:
     for i, nm in enumerate(names):
         print(f"{i:3d} {nm:44s} start {float(start[i]):8.1f} dur {float(dur[i]):6.1f}")
