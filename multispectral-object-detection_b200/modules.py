@@ -98,8 +98,10 @@ class Conv(nn.Module):
         w, b = self.folded(x.device)
         return ops.conv2d(x, w, b, k, s, act, out=out, residual=residual, cout=self.conv.out_channels)
 
-    def fuseforward(self, x):  # reference models/common.py:49-50 (after Model.fuse)
-        return self.forward(x)
+    def fuseforward(self, x, out=None, residual=None):  # reference models/common.py:49-50
+        # the reference's Model.fuse() rebinds `m.forward = m.fuseforward` (models/yolo_test.py:302): go through the class,
+        # not through self.forward, and keep the keyword arguments the sibling modules pass (out= / residual=)
+        return Conv.forward(self, x, out=out, residual=residual)
 
 
 class Focus(nn.Module):
