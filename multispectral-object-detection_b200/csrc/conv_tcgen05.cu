@@ -197,22 +197,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   pdl_launch_dependents();
   if (p.b_res && warp == 0 && elect_one_sync()) {
     // weights are parameters, never written by a predecessor kernel: fetch them before the dependency wait
-    const uint32_t b_unit = static_cast<uint32_t>(b_rows) * static_cast<uint32_t>(p.kelems) * 2u;
-    if (p.halo) {
-      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.b_res_bytes));
-      for (int u = 0; u < p.kw * p.kchunks; ++u) {
-        const int kx = u / p.kchunks, kc = u - kx * p.kchunks;
-        for (int ky = 0; ky < 3; ++ky)
-          tma_load_3d(smem_b + (u * 3 + ky) * b_unit, &maps.b, bres_bar, kc * p.kelems, ky * p.kw + kx, 0);
-      }
-    } else {
-      // 1x1 conv / Linear whose whole [Cout, Cin] matrix fits: K chunk kc at smem_b + kc * b_unit.  A pair splits the rows:
-      // both CTAs credit CTA 0's barrier (the MMA issuer lives there), CTA 0 alone arms it with the pair's byte count.
-      if (rank == 0) mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.b_res_bytes) * kCtas);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        if constexpr (kCtas == 2) tma_load_3d_2sm(smem_b + kc * b_unit, &maps.b, bres_bar, kc * p.kelems, 0, rank * b_rows);
-        else tma_load_3d(smem_b + kc * b_unit, &maps.b, bres_bar, kc * p.kelems, 0, 0);
-      }
+    const uint32_t b_unit = static_cast<uint32_t>(p.block_n) * static_cast<uint32_t>(p.kelems) * 2u;
+    mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.b_res_bytes));
+    for (int u = 0; u < p.kw * p.kchunks; ++u) {
+      const int kx = u / p.kchunks, kc = u - kx * p.kchunks;
+      for (int ky = 0; ky < 3; ++ky)
+        tma_load_3d(smem_b + (u * 3 + ky) * b_unit, &maps.b, bres_bar, kc * p.kelems, ky * p.kw + kx, 0);
     }
   }
   pdl_wait();
@@ -301,16 +291,15 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
             if (elect_one_sync()) {
               uint8_t* sa = smem_a + stage * a_stage_bytes;
               uint8_t* sb = smem_b + stage * b_stage_bytes;
-              const uint32_t tx = p.b_res ? static_cast<uint32_t>(p.TW * p.TH) * row_bytes : tx_unit;   // weights resident: A only
               if constexpr (kCtas == 2) {
                 tma_load_4d_2sm(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
-                if (!p.b_res) tma_load_3d_2sm(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0 + rank * b_rows);
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx);
+                tma_load_3d_2sm(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0 + rank * b_rows);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * tx_unit);
                 else mbar_arrive_cluster(&full_bar[stage], 0);
               } else {
-                mbar_arrive_expect_tx(&full_bar[stage], tx);
+                mbar_arrive_expect_tx(&full_bar[stage], tx_unit);
                 tma_load_4d(sa, &maps.a[mi], &full_bar[stage], kc * p.kelems, t.x0 + dx, t.y0 + dy, t.b);
-                if (!p.b_res) tma_load_3d(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
+                tma_load_3d(sb, &maps.b, &full_bar[stage], kc * p.kelems, tap, t.n0);
               }
             }
             __syncwarp();
@@ -422,8 +411,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
               }
             }
           } else if (p.kelems == 64) {     // one (tap, 64-channel) unit per stage: 4 back-to-back MMAs, no inner loops
-            const uint32_t a_lo = a_lo0 + stage * a_lo_stride;
-            const uint32_t b_lo = p.b_res ? b_lo0 + it * (b_unit_bytes >> 4) : b_lo0 + stage * b_lo_stride;   // resident: K chunk `it`
+            const uint32_t a_lo = a_lo0 + stage * a_lo_stride, b_lo = b_lo0 + stage * b_lo_stride;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {             // +32 B along K inside the swizzle atom = +2 in the address field
               const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
@@ -847,19 +835,6 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     const int bytes = kw * p.kchunks * 3 * p.block_n * p.kelems * 2;
     const int rounded = (bytes + 1023) / 1024 * 1024;
     if (rounded <= 96 * 1024 && (ring_budget - rounded) / p.a_slot >= 3) {
-      p.b_res = rounded;
-      p.b_res_bytes = bytes;
-      p.b_slot = 0;
-    }
-  }
-  // the same for a 1x1 conv / Linear whose whole weight matrix is one n-block: every tile of a CTA multiplies by the same
-  // [block_n, Cin] matrix, so it is loaded once (a pair holds half of the rows each) and the ring streams activations only
-  // -- re-streaming it per tile was half of the L2 -> SM traffic of the P3 / P4 1x1 layers
-  static const bool no_bres1 = getenv("CFT_NO_BRES_1X1") != nullptr;
-  if (!p.halo && p.taps == 1 && p.n_blocks == 1 && p.kelems == 64 && p.ups == 1 && !g_no_bres && !no_bres1 && m_tiles > 2 * sm_count()) {
-    const int bytes = p.kchunks * (p.block_n / ctas) * 128;
-    const int rounded = (bytes + 1023) / 1024 * 1024;
-    if (rounded <= 96 * 1024 && (ring_budget - rounded) / p.a_slot >= 4) {
       p.b_res = rounded;
       p.b_res_bytes = bytes;
       p.b_slot = 0;

@@ -49,12 +49,9 @@ def _check(p, B, H, W, cin, cout, k, s, what, min_stages=2):
     assert p.kelems in (16, 32, 64) and p.kchunks * p.kelems >= cin and (p.kchunks - 1) * p.kelems < cin, what
     assert p.acc_stages * p.acc_cols == TMEM_COLS and p.acc_cols >= p.block_n, what
     assert min_stages <= p.stages <= 8, what                            # a pipeline, within the barrier arrays
-    if p.b_res and p.halo:                                              # whole 3x3 weight matrix resident
-        assert p.ctas == 1 and p.n_blocks == 1 and p.stages >= 3 and p.b_slot == 0, what
-        assert p.b_res >= 9 * p.kchunks * p.block_n * p.kelems * 2 and p.b_res <= 96 * 1024, what
-    elif p.b_res:                                                       # whole 1x1 / Linear weight matrix (half per CTA of a pair)
-        assert k == 1 and p.n_blocks == 1 and p.kelems == 64 and p.ups == 1 and p.stages >= 4 and p.b_slot == 0, what
-        assert p.b_res >= p.kchunks * (p.block_n // p.ctas) * 128 and p.b_res <= 96 * 1024, what
+    if p.b_res:
+        assert p.halo and p.ctas == 1 and p.n_blocks == 1 and p.stages >= 3 and p.b_slot == 0, what
+        assert p.b_res >= 9 * p.kchunks * p.block_n * p.kelems * 2 and p.b_res <= 96 * 1024, what   # whole 3x3 weight matrix
     if p.halo:
         assert k == 3 and s == 1 and wo % 8 == 0 and ho % 16 == 0 and (p.TW, p.TH) == (8, 16), what
         assert p.a_slot >= p.ups * (p.TH + 2) * p.TW * p.kelems * 2, what

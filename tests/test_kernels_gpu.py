@@ -58,9 +58,6 @@ CONV_CASES = [
     (2, 32, 64, 24, 40, 3, 1, 1, True),         # 64 B operand rows (SWIZZLE_64B ring), residual via TMA
     (2, 16, 32, 32, 32, 3, 2, 1, False),        # 32 B operand rows (SWIZZLE_32B ring), stride 2
     (1, 64, 96, 20, 20, 3, 1, 1, True),         # 3 column chunks: uneven split over the 2 epilogue groups
-    (8, 128, 128, 80, 80, 1, 1, 1, False),      # 400 flat tiles: whole 1x1 weight matrix resident in smem (single CTA)
-    (8, 256, 256, 80, 80, 1, 1, 1, False),      # the same with CTA pairs: each CTA keeps half of the rows
-    (4, 64, 128, 160, 160, 1, 1, 1, False),     # cv1||cv2-style N = 128, K = 64 (one resident K chunk)
     (32, 128, 128, 80, 80, 3, 1, 1, True),      # full-size C3 bottleneck conv (batch 32): many tiles per CTA
 ]
 
