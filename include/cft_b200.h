@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFT_ABI_VERSION 5
+#define CFT_ABI_VERSION 6
 
 enum {
   CFT_OK = 0,
@@ -72,6 +72,12 @@ typedef struct cft_conv_args {
   const void* res; int ldr, r_coff;
   void* y; int ldy, y_coff, out_dtype;
   int kw;
+  /* Optional chained 1x1 (back-to-back GEMM in the epilogue): y2 = act2(w2 . y + bias2) per output pixel, computed from the
+   * finished bf16 tile of y while it is still on chip -- a Bottleneck's cv1 (models/common.py:104-106) fused into the conv that
+   * produces its input.  w2: bf16 packed [Cout][1][Cout] (NULL = no chain); y2: bf16 NHWC channel slice [y2_coff, y2_coff+Cout)
+   * of a tensor with the geometry of y; skip_y != 0: y itself is not written (only y2 is wanted).  Needs out_dtype bf16 and
+   * Cout in {64, 128}; otherwise CFT_E_UNSUPPORTED and the caller launches the 1x1 separately. */
+  const void* w2; const float* bias2; void* y2; int ldy2, y2_coff, act2, skip_y;
 } cft_conv_args;
 
 /* tcgen05 / TMA / TMEM implicit-GEMM kernel (the product path). */

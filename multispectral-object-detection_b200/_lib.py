@@ -31,6 +31,8 @@ class ConvArgs(C.Structure):
         ("res", C.c_void_p), ("ldr", C.c_int), ("r_coff", C.c_int),
         ("y", C.c_void_p), ("ldy", C.c_int), ("y_coff", C.c_int), ("out_dtype", C.c_int),
         ("kw", C.c_int),
+        ("w2", C.c_void_p), ("bias2", C.c_void_p), ("y2", C.c_void_p), ("ldy2", C.c_int), ("y2_coff", C.c_int),
+        ("act2", C.c_int), ("skip_y", C.c_int),
     ]
 
 

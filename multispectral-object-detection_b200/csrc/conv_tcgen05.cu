@@ -44,13 +44,16 @@ constexpr int kTmemCols = 512;
 constexpr int kSmemTotal = 227 * 1024;    // dynamic smem per CTA on sm_100
 constexpr int kStageCBytes = 16 * 1024;   // one epilogue staging buffer (128 rows x 128 B)
 
-constexpr int kTailBytes = 256 + 2048;     // barriers + TMEM slot, bias staging (one copy per epilogue team)
+constexpr int kTailBytes = 256 + 2048 + 64 + 1024;   // barriers + TMEM slot | bias staging (one copy per epilogue team) |
+                                                     // chain-mode barriers | bias of the chained 1x1 (one copy per team)
 
 struct __align__(64) TensorMaps {
   CUtensorMap a[4];
   CUtensorMap b;
-  CUtensorMap c;   // output (TMA store), box (32 channels, TW, TH, 1)
+  CUtensorMap c;   // output (TMA store), box (32 channels, TW, TH, 1); chain mode: 64-channel SWIZZLE_128B boxes
   CUtensorMap r;   // residual (TMA load), same geometry as c
+  CUtensorMap b2;  // chain mode: weights of the chained 1x1, box (64, 1, Cout / ctas)
+  CUtensorMap c2;  // chain mode: output of the chained 1x1, same geometry as c
 };
 
 struct ConvParams {
@@ -71,6 +74,11 @@ struct ConvParams {
   unsigned long long* span;    // debug (cft_debug_conv_spans): {min CTA start, max CTA end} of this launch in %globaltimer ns
   unsigned long long* trace;   // debug timeline (cft_debug_conv_trace): kTraceSlots clock samples per CTA, else null
   int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
+  // chain mode (back-to-back GEMM): y2 = act2(W2 . y + bias2) per pixel, computed from the finished bf16 output tile while
+  // it sits in the TMA-store staging buffer (= a K-major SWIZZLE_128B UMMA operand) -- a Bottleneck's cv1 fused into the conv
+  // that produces its input (models/common.py:99-109).  Cout in {64, 128}, one n-block, W2 = [Cout, Cout] resident in smem.
+  int chain, k2chunks, act2, store_main, w2_bytes;
+  const float* bias2;
   int TW, TH, tiles_x, tiles_y;
   int n_blocks, block_n, num_tiles, stages;
   uint32_t mg_nb, mg_tx, mg_ty;   // ceil(2^32 / d) for n_blocks, tiles_x, tiles_y (0 = divide)
@@ -123,6 +131,34 @@ __device__ __forceinline__ void trace_mark(const ConvParams& p, int slot) {
   if (p.trace != nullptr && slot < kTraceSlots) p.trace[blockIdx.x * kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
 }
 
+// 32 accumulator columns -> act(acc + bias); bias staged in smem (pre-halved for the tanh-SiLU code 3)
+__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float* bias, int act, float (&f)[32]) {
+  const float4* bs = reinterpret_cast<const float4*>(bias);
+  if (act == 3) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b4 = bs[i];
+      f[4 * i + 0] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 0]), 0.5f, b4.x));
+      f[4 * i + 1] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, b4.y));
+      f[4 * i + 2] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, b4.z));
+      f[4 * i + 3] = silu_tanh_h(fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, b4.w));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b4 = bs[i];
+      f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+      f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+      f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+      f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+    }
+    if (act == CFT_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = silu_fast(f[i]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -143,7 +179,8 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.b_slot);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * a_stage_bytes;
-  uint8_t* smem_c = smem_b + (p.b_res ? p.b_res : stages * b_stage_bytes);  // both multiples of 1024
+  uint8_t* smem_w2 = smem_b + (p.b_res ? p.b_res : stages * b_stage_bytes);  // both multiples of 1024
+  uint8_t* smem_c = smem_w2 + p.w2_bytes;                                    // chain mode: W2 resident in front of the staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + kEpiGroups * p.stage_c);
   uint64_t* full_bar = bars;                          // [kMaxStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]  MMA -> TMA
@@ -153,6 +190,11 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
   uint64_t* bres_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups;   // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 1);
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2 * kMaxAccStages + kEpiGroups + 4);   // [2][256] bias, 16 B aligned
+  uint64_t* a2_ready = reinterpret_cast<uint64_t*>(bias_s + 512);   // [2] chain: team's output tile is an operand now
+  uint64_t* acc2_full = a2_ready + 2;                               // [2] chain: second accumulator of the team ready
+  uint64_t* acc2_empty = a2_ready + 4;                              // [2] chain: ... drained
+  uint64_t* w2_bar = a2_ready + 6;                                  // chain: W2 landed
+  float* bias2_s = reinterpret_cast<float*>(a2_ready + 8);          // [2][128]
 
   if (threadIdx.x == 0) {
     if (p.span != nullptr) {
@@ -180,6 +222,12 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     }
     for (int i = 0; i < kEpiGroups; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(bres_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a2_ready[i], kCtas);                               // the team leader of each CTA of the pair
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_empty[i], (kEpilogueWarps / 2) * kCtas);
+    }
+    mbar_init(w2_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -203,6 +251,17 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       const int kx = u / p.kchunks, kc = u - kx * p.kchunks;
       for (int ky = 0; ky < 3; ++ky)
         tma_load_3d(smem_b + (u * 3 + ky) * b_unit, &maps.b, bres_bar, kc * p.kelems, ky * p.kw + kx, 0);
+    }
+  }
+  if (p.chain && warp == 0 && elect_one_sync()) {
+    // weights of the chained 1x1: [Cout, Cout], K chunk kc of this CTA's rows at smem_w2 + kc * unit.  A pair splits the rows;
+    // both CTAs credit CTA 0's barrier (the MMA issuer lives there), CTA 0 alone arms it with the pair's byte count.
+    const int w2rows = p.Cout / kCtas;
+    const uint32_t unit = static_cast<uint32_t>(w2rows) * 128u;
+    if (rank == 0) mbar_arrive_expect_tx(w2_bar, unit * static_cast<uint32_t>(p.k2chunks) * kCtas);
+    for (int kc = 0; kc < p.k2chunks; ++kc) {
+      if constexpr (kCtas == 2) tma_load_3d_2sm(smem_w2 + kc * unit, &maps.b2, w2_bar, kc * 64, 0, rank * w2rows);
+      else tma_load_3d(smem_w2 + kc * unit, &maps.b2, w2_bar, kc * 64, 0, 0);
     }
   }
   pdl_wait();
@@ -362,6 +421,41 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       tc_fence_after();
     }
     long long w_full = 0, w_empty = 0, c0 = 0;     // debug trace: cycles this warp waited for operands / accumulators
+    // chain mode: the second GEMM of tile jj (the team's finished bf16 output tile x W2) is issued behind the main MMAs of
+    // tile jj + 1, by which time the team's first epilogue has normally turned the tile into an operand
+    int jt = 0;
+    bool w2_seen = false;
+    auto issue_gemm2 = [&](int jj) {
+      const int tm = jj & 1;
+      const uint32_t par = static_cast<uint32_t>(jj >> 1) & 1u;
+      if (!w2_seen) {
+        mbar_wait(w2_bar, 0);
+        w2_seen = true;
+      }
+      mbar_wait(&a2_ready[tm], par);
+      mbar_wait(&acc2_empty[tm], par ^ 1u);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t idesc2 = umma_idesc_ex(128u * kCtas, static_cast<uint32_t>(p.Cout), 0, 0);
+        constexpr uint32_t hi128 = (1024u >> 4) | (1u << 14) | (2u << 29);           // SBO 1024 B, SWIZZLE_128B
+        const uint32_t a2_lo = smem_u32(smem_c + tm * (p.k2chunks * 16384)) >> 4;
+        const uint32_t w2_lo = smem_u32(smem_w2) >> 4;
+        const uint32_t w2_unit16 = (static_cast<uint32_t>(p.Cout / kCtas) * 128u) >> 4;
+        const uint32_t d2 = tmem_base + 256u + 128u * tm;
+        for (int kc = 0; kc < p.k2chunks; ++kc) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = (static_cast<uint64_t>(hi128) << 32) | (a2_lo + kc * 1024 + 2 * k);
+            const uint64_t db = (static_cast<uint64_t>(hi128) << 32) | (w2_lo + kc * w2_unit16 + 2 * k);
+            if constexpr (kCtas == 2) umma_bf16_2sm(d2, da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
+            else umma_bf16(d2, da, db, idesc2, (kc | k) != 0 ? 1u : 0u);
+          }
+        }
+        if constexpr (kCtas == 2) umma_commit_2sm(&acc2_full[tm]);
+        else umma_commit(&acc2_full[tm]);
+      }
+      __syncwarp();
+    };
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       if (p.trace) c0 = clock64();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -452,7 +546,10 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         acc = 0;
         acc_phase ^= 1u;
       }
+      if (p.chain && jt >= 1) issue_gemm2(jt - 1);
+      ++jt;
     }
+    if (p.chain && jt >= 1) issue_gemm2(jt - 1);
     if (p.trace && lane == 0) {
       p.trace[blockIdx.x * kTraceSlots + kTraceSlots - 2] = static_cast<unsigned long long>(w_full);
       p.trace[blockIdx.x * kTraceSlots + kTraceSlots - 3] = static_cast<unsigned long long>(w_empty);
@@ -481,6 +578,113 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     int bias_n0 = -1;
     const int bar_id = 1 + grp;
     const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages == 4 ? 2 : 1;
+    if (p.chain) {
+      // ===================== chain mode: y -> staging tile (a UMMA operand) -> second GEMM -> y2 =====================
+      // 2 teams x (2 column groups x 4 warps); team t drains tiles t, t + 2, ... of this CTA: main accumulator `t`
+      // (2 x 128 columns), second accumulator 256 + 128 t.  The team's staging buffer A2 holds the finished bf16 tile as
+      // Cout / 64 boxes of (64 channels x TW x TH) in SWIZZLE_128B = K-major UMMA chunks of 128 rows x 128 B: it is the
+      // source of the TMA store of y AND the A operand of the second GEMM; its result (y2) reuses the buffer.
+      const int ttid = cg * 128 + gtid;                  // thread within the team
+      const bool leader = ttid == 0;
+      const int n64 = p.k2chunks;                        // 64-channel boxes per tile
+      uint8_t* A2 = smem_c + team * (n64 * 16384);
+      float* bias2_t = bias2_s + team * 128;
+      uint64_t* rb = &res_bar[team];
+      const uint32_t box_bytes = static_cast<uint32_t>(p.TW * p.TH) * 128u;
+      const int nch = p.Cout >> 5;                       // 32-column chunks; this column group: cg, cg + 2
+      const int tbar = 8 + team;
+      const uint32_t lane_q = static_cast<uint32_t>(q * 32) << 16;
+      for (int i = ttid; i < p.Cout; i += 256) {         // both bias vectors, once (one n-block)
+        const float b1 = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
+        const float b2 = p.bias2 != nullptr ? __ldg(p.bias2 + i) : 0.f;
+        bias_t[i] = p.act == 3 ? 0.5f * b1 : b1;
+        bias2_t[i] = p.act2 == 3 ? 0.5f * b2 : b2;
+      }
+      for (int j = team;; j += 2) {
+        const int tile = work0 + j * work_stride;
+        if (tile >= p.num_tiles) break;
+        const uint32_t par = static_cast<uint32_t>(j >> 1) & 1u;          // this team's (j / 2)-th tile
+        const TileCoord t = decode_tile<kCtas>(p, tile, rank);
+        if (leader) {
+          bulk_wait_read<0>();                                           // the previous y2 store has read A2
+          if (use_res) {
+            mbar_arrive_expect_tx(rb, static_cast<uint32_t>(n64) * box_bytes);
+            for (int c = 0; c < n64; ++c) tma_load_4d(A2 + c * 16384, &maps.r, rb, c * 64, t.x0, t.y0, t.b);
+          }
+        }
+        named_bar_sync(tbar, 256);
+        mbar_wait(&tfull_bar[team], par);
+        tc_fence_after();
+        if (use_res) {
+          mbar_wait(rb, res_phase);
+          res_phase ^= 1u;
+        }
+        for (int ci = cg; ci < nch; ci += 2) {
+          const int c0 = ci * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_q + static_cast<uint32_t>(team * 128 + c0), v);
+          float f[32];
+          bias_act32(v, bias_t + c0, p.act, f);
+          uint8_t* rowp = A2 + (c0 >> 6) * 16384 + row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            bf16x8* s0 = reinterpret_cast<bf16x8*>(rowp + (((((c0 & 63) >> 3) + ch) ^ (row & 7)) << 4));
+            if (use_res) {
+              float r[8];
+              unpack8(*s0, r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[8 * ch + i] += r[i];
+            }
+            *s0 = pack8(f + 8 * ch);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&tempty_bar[team], 0);
+          else mbar_arrive(&tempty_bar[team]);
+        }
+        fence_proxy_async();
+        named_bar_sync(tbar, 256);
+        if (leader) {
+          if (p.store_main) {
+            for (int c = 0; c < n64; ++c) tma_store_4d(&maps.c, A2 + c * 16384, c * 64, t.x0, t.y0, t.b);
+            bulk_commit();
+          }
+          if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&a2_ready[team], 0);      // the tile is an operand now
+          else mbar_arrive(&a2_ready[team]);
+        }
+        // ---- the chained 1x1: second accumulator -> act2(acc + bias2) -> y2
+        mbar_wait(&acc2_full[team], par);
+        tc_fence_after();
+        if (leader) bulk_wait_read<0>();                                 // the store of y has read A2 (GEMM 2 has, too)
+        named_bar_sync(tbar, 256);
+        for (int ci = cg; ci < nch; ci += 2) {
+          const int c0 = ci * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_q + static_cast<uint32_t>(256 + team * 128 + c0), v);
+          float f[32];
+          bias_act32(v, bias2_t + c0, p.act2, f);
+          uint8_t* rowp = A2 + (c0 >> 6) * 16384 + row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<bf16x8*>(rowp + (((((c0 & 63) >> 3) + ch) ^ (row & 7)) << 4)) = pack8(f + 8 * ch);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2 && rank != 0) mbar_arrive_cluster(&acc2_empty[team], 0);
+          else mbar_arrive(&acc2_empty[team]);
+        }
+        fence_proxy_async();
+        named_bar_sync(tbar, 256);
+        if (leader) {
+          for (int c = 0; c < n64; ++c) tma_store_4d(&maps.c2, A2 + c * 16384, c * 64, t.x0, t.y0, t.b);
+          bulk_commit();
+        }
+      }
+      if (leader) bulk_wait_all();
+    } else
     for (int j = team;; j += teams) {          // j = index in this CTA's tile sequence (the MMA warp walks all j)
       const int tile = work0 + j * work_stride;
       if (tile >= p.num_tiles) break;
@@ -744,6 +948,16 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
               "cft_conv2d: pointers must be 16-byte aligned");
   CFT_REQUIRE(a->stride == 1 || (a->H % 2 == 0 && a->W % 2 == 0), "cft_conv2d: stride 2 needs even H, W");
   CFT_REQUIRE(a->out_dtype == CFT_DT_BF16 || a->out_dtype == CFT_DT_F32, "cft_conv2d: bad out_dtype");
+  const bool chain = a->w2 != nullptr;
+  if (chain) {
+    CFT_REQUIRE(a->y2 != nullptr && a->ldy2 % 8 == 0 && a->y2_coff % 8 == 0 && a->y2_coff + a->Cout <= a->ldy2 &&
+                    reinterpret_cast<uintptr_t>(a->y2) % 16 == 0 && reinterpret_cast<uintptr_t>(a->w2) % 16 == 0,
+                "cft_conv2d: chained 1x1: bad y2 / w2 (null, misaligned or channel slice out of range)");
+    if (a->out_dtype != CFT_DT_BF16 || (a->Cout != 64 && a->Cout != 128)) {
+      set_error("cft_conv2d: chained 1x1 needs a bf16 output with 64 or 128 channels (got %d)", a->Cout);
+      return CFT_E_UNSUPPORTED;
+    }
+  }
 
   // A 1x1 stride-1 conv has no halo: walk its pixels as one flat [B*H*W, C] matrix, so that tiles are 128
   // consecutive pixels (40x40 and 20x20 maps otherwise leave 11 % / 22 % of every 128-row MMA tile empty).
@@ -787,8 +1001,8 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
          p.block_n >= 128 && (p.block_n / 2) % 32 == 0 && a->Cout % (p.block_n / 2) == 0)
     p.block_n /= 2;
   p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
-  p.acc_stages = (p.block_n <= 128 && !g_acc2) ? 4 : 2;
-  p.acc_cols = 512 / p.acc_stages;
+  p.acc_stages = (p.block_n <= 128 && !g_acc2 && !chain) ? 4 : 2;
+  p.acc_cols = chain ? 128 : 512 / p.acc_stages;      // chain mode: main 2 x 128 columns, second accumulators at 256 + 128 t
   CFT_REQUIRE(m_tiles * p.n_blocks < (1LL << 31), "cft_conv2d: too many tiles");
   p.m_tiles = static_cast<int>(m_tiles);
   // CTA pairs (cta_group::2, UMMA M = 256): each CTA stages only half of the weight tile, halving the smem
@@ -819,12 +1033,19 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   // small batch): the tail after the last MMA is then one tile drained by 16 warps instead of 8
   {
     const int units0 = sm_count() / ctas;
-    p.teams = (g_one_team && p.num_tiles <= units0) ? 1 : kEpiTeams;
+    p.teams = (g_one_team && !chain && p.num_tiles <= units0) ? 1 : kEpiTeams;
   }
+  p.chain = chain ? 1 : 0;
+  p.k2chunks = chain ? a->Cout / 64 : 0;
+  p.act2 = (a->act2 == CFT_ACT_SILU && g_silu_tanh) ? 3 : a->act2;
+  p.store_main = a->skip_y ? 0 : 1;
+  p.bias2 = a->bias2;
+  p.w2_bytes = chain ? (a->Cout / ctas) * a->Cout * 2 : 0;         // [Cout / ctas rows][Cout] bf16, a multiple of 1 KiB
   const int col_groups_h = kEpiGroups / p.teams;
   const int chunks_per_group = ((p.block_n + 31) / 32 + col_groups_h - 1) / col_groups_h;
   p.stage_c = (!p.out_f32 && (chunks_per_group <= 1 || g_stage8k)) ? 8 * 1024 : kStageCBytes;
-  const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * p.stage_c;
+  if (chain) p.stage_c = a->Cout * 128 / 2;       // 4 x stage_c = the two teams' [128 px x Cout] bf16 tiles (8 / 16 KiB each)
+  const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * p.stage_c - p.w2_bytes;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;
   p.b_slot = p.halo ? ((p.ups * 3 * (p.block_n / ctas) * p.kelems * 2 + 1023) / 1024) * 1024 : (p.block_n / ctas) * 128;
   // small weight matrices (3x3 convs up to 64 -> 64) stay resident in smem for the whole kernel: they were half of the
@@ -860,7 +1081,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     o->kelems = p.kelems; o->kchunks = p.kchunks; o->ups = p.ups; o->halo = p.halo;
     o->stages = p.stages; o->a_slot = p.a_slot; o->b_slot = p.b_slot; o->b_res = p.b_res;
     o->acc_stages = p.acc_stages; o->acc_cols = p.acc_cols; o->teams = p.teams; o->stage_c = p.stage_c;
-    o->smem_bytes = 1024 + p.stages * stage_bytes + p.b_res + kEpiGroups * p.stage_c + kTailBytes;
+    o->smem_bytes = 1024 + p.stages * stage_bytes + p.b_res + p.w2_bytes + kEpiGroups * p.stage_c + kTailBytes;
     int units_p = sm_count() / ctas;
     if (units_p > p.num_tiles) units_p = p.num_tiles;
     o->grid = units_p * ctas;
@@ -912,22 +1133,32 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     const uint8_t* yb = reinterpret_cast<const uint8_t*>(a->y) + static_cast<size_t>(a->y_coff) * es;
     cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)a->B};
     cuuint64_t str[3] = {(cuuint64_t)a->ldy * es, (cuuint64_t)p.Wo * a->ldy * es, (cuuint64_t)p.Ho * p.Wo * a->ldy * es};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t box[4] = {chain ? 64u : 32u, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    const CUtensorMapSwizzle c_swz = (p.out_f32 || chain) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     rc = encode_map(&maps.c, yb, 4, dims, str, box,
-                    p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                    p.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+                    p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c_swz);
     if (rc) return rc;
+    if (chain) {
+      const uint8_t* y2b = reinterpret_cast<const uint8_t*>(a->y2) + static_cast<size_t>(a->y2_coff) * es;
+      cuuint64_t str2[3] = {(cuuint64_t)a->ldy2 * es, (cuuint64_t)p.Wo * a->ldy2 * es, (cuuint64_t)p.Ho * p.Wo * a->ldy2 * es};
+      rc = encode_map(&maps.c2, y2b, 4, dims, str2, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c_swz);
+      if (rc) return rc;
+      cuuint64_t wd[3] = {(cuuint64_t)a->Cout, 1, (cuuint64_t)a->Cout};
+      cuuint64_t ws[2] = {(cuuint64_t)a->Cout * 2, (cuuint64_t)a->Cout * 2};
+      cuuint32_t wb[3] = {64, 1, (cuuint32_t)(a->Cout / ctas)};
+      rc = encode_map(&maps.b2, a->w2, 3, wd, ws, wb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
     if (a->res) {
       const uint8_t* rb = reinterpret_cast<const uint8_t*>(a->res) + static_cast<size_t>(a->r_coff) * es;
       cuuint64_t rstr[3] = {(cuuint64_t)a->ldr * es, (cuuint64_t)p.Wo * a->ldr * es, (cuuint64_t)p.Ho * p.Wo * a->ldr * es};
       rc = encode_map(&maps.r, rb, 4, dims, rstr, box,
-                      p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                      p.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+                      p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c_swz);
       if (rc) return rc;
     }
   }
 
-  const int smem_bytes = 1024 + p.stages * stage_bytes + p.b_res + kEpiGroups * p.stage_c + kTailBytes;
+  const int smem_bytes = 1024 + p.stages * stage_bytes + p.b_res + p.w2_bytes + kEpiGroups * p.stage_c + kTailBytes;
   if (!g_attr_set) {
     const int max_smem = kSmemTotal;
     rc = check_cuda(cudaFuncSetAttribute(cft_conv_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),

@@ -205,9 +205,39 @@ class C3(nn.Module):
         cat = ops.conv2d(x, w12, b12, 1, 1, ACT_SILU, cout=2 * c_)        # [cv1(x) | cv2(x)]
         a = cat[:, :c_]
         n = len(self.m)
+        if self.chain and n >= 2 and ops.conv_chain_supported(c_) and all(self._chainable(b, c_) for b in self.m):
+            # every Bottleneck's cv1 (1x1) except the first rides in the epilogue of the previous Bottleneck's cv2 (3x3) as a
+            # back-to-back GEMM on the on-chip output tile: n - 1 launches and as many re-reads of `a` fewer per C3
+            t = self.m[0].cv1(a)
+            for j, blk in enumerate(self.m):
+                w3, b3 = blk.cv2.folded(x.device)
+                res = a if blk.add else None
+                if j == n - 1:
+                    a = ops.conv2d(t, w3, b3, 3, 1, ACT_SILU, out=cat[:, :c_], residual=res, cout=c_)
+                else:
+                    nxt = self.m[j + 1]
+                    w1, b1 = nxt.cv1.folded(x.device)
+                    a, t = ops.conv2d(t, w3, b3, 3, 1, ACT_SILU, residual=res, cout=c_, chain=(w1, b1, ACT_SILU, None),
+                                      skip_out=not nxt.add)         # a' is only read again as the next residual
+            return self.cv3(cat, out=out)
         for j, blk in enumerate(self.m):
             a = blk(a, out=cat[:, :c_] if j == n - 1 else None)
         return self.cv3(cat, out=out)
+
+    # Bottleneck cv1 fused into the preceding 3x3 (csrc/conv_tcgen05.cu, chain mode); CFT_NO_CONV_CHAIN=1 / chain = False
+    # launches every 1x1 separately
+    chain = os.environ.get("CFT_NO_CONV_CHAIN") is None
+
+    @staticmethod
+    def _chainable(blk, c_):
+        try:
+            k1, s1, a1 = blk.cv1._check()
+            k2, s2, a2 = blk.cv2._check()
+        except CftError:
+            return False
+        _require_eval_bn(getattr(blk.cv1, "bn", None)), _require_eval_bn(getattr(blk.cv2, "bn", None))
+        return (k1, s1, a1, k2, s2, a2) == (1, 1, ACT_SILU, 3, 1, ACT_SILU) and blk.cv1.conv.in_channels == c_ \
+            and blk.cv1.conv.out_channels == c_ and blk.cv2.conv.out_channels == c_
 
 
 class SPP(nn.Module):

@@ -96,11 +96,19 @@ def pack_linear_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device=Non
 
 
 # ------------------------------------------------------------------------------ conv / gemm
+def conv_chain_supported(cout: int) -> bool:
+    """Can a 1x1 with ``cout`` -> ``cout`` channels ride in the epilogue of the conv that produces its input?"""
+    return cout in (64, 128)
+
+
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, act: int,
            out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, cout: Optional[int] = None,
-           cin: Optional[int] = None, impl: str = "tcgen05", kw: int = 0) -> torch.Tensor:
+           cin: Optional[int] = None, impl: str = "tcgen05", kw: int = 0, chain=None, skip_out: bool = False):
     """y = act(conv(x, w) + bias) [+ residual] on NHWC bf16; ``out`` may be a channel-slice view.
-    ``k`` is the kernel height, ``kw`` its width (0 = square)."""
+    ``k`` is the kernel height, ``kw`` its width (0 = square).
+    ``chain = (w2, bias2, act2, out2)``: additionally y2 = act2(w2 . y + bias2) (a 1x1 with Cout -> Cout channels, weights
+    from ``pack_conv_weight``) computed in the same launch from the on-chip tile of y; returns ``(y, y2)``.  ``skip_out``:
+    y is not written (``None`` is returned in its place)."""
     lib = _lib.lib()
     xp, ldx = nhwc_desc(x)
     b, c, h, wd = x.shape
@@ -123,8 +131,21 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: in
         a.res, a.ldr, a.r_coff = None, 0, 0
     a.y, a.ldy, a.y_coff, a.out_dtype = yp, ldy, 0, DT_BF16
     a.kw = kw
+    out2 = None
+    if chain is not None:
+        w2, bias2, act2, out2 = chain
+        if out2 is None:
+            out2 = empty_nhwc(b, cout, ho, wo, x.device)
+        y2p, ldy2 = nhwc_desc(out2)
+        if tuple(out2.shape) != (b, cout, ho, wo) or tuple(w2.shape[:1]) != (cout,):
+            raise _lib.CftError(f"conv2d: chained 1x1 needs out2 {(b, cout, ho, wo)} and a [{cout}, 1, {cout}] weight")
+        a.w2, a.bias2, a.y2, a.ldy2, a.y2_coff, a.act2 = w2.data_ptr(), (bias2.data_ptr() if bias2 is not None else None), \
+            y2p, ldy2, 0, act2
+        a.skip_y = 1 if skip_out else 0
     fn = lib.cft_conv2d if impl == "tcgen05" else lib.cft_conv2d_ref
     _lib.check(fn(C.byref(a), _stream()), "cft_conv2d")
+    if chain is not None:
+        return (None if skip_out else out), out2
     return out
 
 

@@ -60,7 +60,7 @@ def _check(p, B, H, W, cin, cout, k, s, what, min_stages=2):
     assert p.a_slot % 1024 == 0 and p.b_slot % 1024 == 0 and p.b_res % 1024 == 0, what   # swizzle-atom alignment
     assert p.teams in (1, 2) and p.stage_c in (8192, 16384), what
     assert p.smem_bytes <= SMEM_MAX, (what, p.smem_bytes)
-    assert p.smem_bytes == 1024 + p.stages * (p.a_slot + p.b_slot) + p.b_res + 4 * p.stage_c + 2304, what
+    assert p.smem_bytes == 1024 + p.stages * (p.a_slot + p.b_slot) + p.b_res + 4 * p.stage_c + 3392, what
     assert 1 <= p.grid <= 148 and p.grid % p.ctas == 0, what
 
 

@@ -281,6 +281,74 @@ def test_upsample_add_copy(cft):
     assert torch.equal(s.float(), (a.float() + b.float()).to(torch.bfloat16).float())
 
 
+CHAIN_CASES = [
+    # B, C, H, W, k, s, residual, skip_out
+    (2, 64, 32, 32, 3, 1, True, False),        # P2-style: row-reuse tiles, resident 3x3 weights, single CTA, N = 64
+    (2, 128, 32, 32, 3, 1, True, False),       # P3-style: row-reuse tiles, CTA pairs (second GEMM as cta_group::2, M = 256)
+    (1, 128, 20, 20, 3, 1, False, False),      # plain 3x3 path (20 is no multiple of 8), pairs, clipped tiles
+    (2, 64, 24, 40, 1, 1, False, False),       # chained behind a flat 1x1
+    (3, 128, 16, 16, 3, 1, False, True),       # y itself not written (head Bottlenecks without shortcut)
+    (8, 128, 80, 80, 3, 1, True, False),       # 800 tiles: both teams, many tiles per CTA, accumulator / staging reuse
+    (8, 64, 160, 160, 3, 1, True, False),      # the yolov5l P2 Bottleneck shape at batch 8
+    (5, 128, 32, 24, 3, 2, False, False),      # stride-2 producer
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,k,s,res,skip", CHAIN_CASES)
+def test_conv_chained_1x1(B, C, H, W, k, s, res, skip, cft):
+    """Back-to-back GEMM: y = SiLU(conv(x) + b) (+ residual), y2 = SiLU(W2 . bf16(y) + b2) in ONE launch (a Bottleneck's cv1
+    fused into the producer of its input, models/common.py:104-106) vs fp32 torch on the same bf16-rounded operands, and vs
+    the two separate launches of the same library (which round at the same places)."""
+    ops = cft.ops
+    x = nhwc(rnd(B, C, H, W, seed=1))
+    w = rnd(C, C, k, k, seed=2, scale=1.0 / math.sqrt(C * k * k))
+    b = rnd(C, seed=3, scale=0.2)
+    w2 = rnd(C, C, 1, 1, seed=4, scale=1.0 / math.sqrt(C))
+    b2 = rnd(C, seed=5, scale=0.2)
+    ho, wo = (H + s - 1) // s, (W + s - 1) // s
+    r = nhwc(rnd(B, C, ho, wo, seed=6)) if res else None
+    wp, bp = ops.pack_conv_weight(w, b, None, device=DEV)
+    w2p, b2p = ops.pack_conv_weight(w2, b2, None, device=DEV)
+    y, y2 = ops.conv2d(x, wp, bp, k, s, 1, residual=r, cout=C, chain=(w2p, b2p, 1, None), skip_out=skip)
+    y_sep = ops.conv2d(x, wp, bp, k, s, 1, residual=r, cout=C)
+    y2_sep = ops.conv2d(y_sep, w2p, b2p, 1, 1, 1, cout=C)
+    torch.cuda.synchronize()
+    y_ref = conv_ref(x.float().cpu(), w.to(torch.bfloat16), b, k, s, 1, r.float().cpu() if res else None)
+    y2_ref = conv_ref(y_ref.to(torch.bfloat16), w2.to(torch.bfloat16), b2, 1, 1, 1)
+    assert (y is None) == skip
+    if not skip:
+        close_bf16(y.cpu(), y_ref, "chain y")
+        assert torch.equal(y, y_sep)
+    close_bf16(y2.cpu(), y2_ref, "chain y2")
+    assert float((y2.float() - y2_sep.float()).abs().max()) <= 2e-2 * float(y2_sep.float().abs().max())
+
+
+def test_c3_chain_equals_separate_launches(cft):
+    """C3 with the Bottleneck cv1s chained into the 3x3 epilogues == the same C3 launching every conv separately."""
+    torch.manual_seed(0)
+    for c, n, shortcut, hw in ((128, 3, True, 32), (256, 4, True, 32), (256, 3, False, 16)):
+        m = cft.modules.C3(c, c, n, shortcut).eval()
+        with torch.no_grad():
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.running_var.uniform_(0.5, 1.5)
+                    mod.running_mean.normal_(0, 0.1)
+                    mod.weight.uniform_(0.5, 1.5)
+                    mod.bias.normal_(0, 0.1)
+        m = m.to(DEV)
+        x = nhwc(rnd(2, c, hw, hw, seed=c))
+        n0 = cft._lib.launch_count()
+        y_chain = m(x)
+        n1 = cft._lib.launch_count()
+        m.chain = False
+        y_sep = m(x)
+        n2 = cft._lib.launch_count()
+        torch.cuda.synchronize()
+        assert (n2 - n1) - (n1 - n0) == n - 1                       # n - 1 launches fewer
+        d = float((y_chain.float() - y_sep.float()).abs().max() / y_sep.float().abs().max())
+        assert d <= 2e-2, (c, n, d)
+
+
 @pytest.mark.parametrize("H,W,C", [(80, 80, 256), (20, 20, 512), (16, 20, 128), (12, 8, 64)])
 def test_gpt_pool_tokens(H, W, C, cft):
     """AdaptiveAvgPool2d((8,8)) incl. the overlapping non-uniform bins of 20->8."""
