@@ -1044,7 +1044,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   const int col_groups_h = kEpiGroups / p.teams;
   const int chunks_per_group = ((p.block_n + 31) / 32 + col_groups_h - 1) / col_groups_h;
   p.stage_c = (!p.out_f32 && (chunks_per_group <= 1 || g_stage8k)) ? 8 * 1024 : kStageCBytes;
-  if (chain) p.stage_c = a->Cout * 128 / 2;       // 4 x stage_c = the two teams' [128 px x Cout] bf16 tiles (8 / 16 KiB each)
+  if (chain) p.stage_c = a->Cout * 128;           // 4 x stage_c = the two teams' [128 px x Cout] bf16 tiles (2 x 16 / 32 KiB)
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * p.stage_c - p.w2_bytes;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;
   p.b_slot = p.halo ? ((p.ups * 3 * (p.block_n / ctas) * p.kelems * 2 + 1023) / 1024) * 1024 : (p.block_n / ctas) * 128;
