@@ -23,10 +23,13 @@ names = []
 orig_conv, orig_gemm = ops.conv2d, ops.gemm
 
 
-def conv_wrap(x, w, bias, k, stride, act, out=None, residual=None, cout=None, cin=None, impl="tcgen05", kw=0):
+def conv_wrap(x, w, bias, k, stride, act, out=None, residual=None, cout=None, cin=None, impl="tcgen05", kw=0, chain=None,
+              skip_out=False):
     b, c, h, wd = x.shape
-    names.append(f"conv {cin or c:4d}->{cout or w.shape[0]:4d} k{k}s{stride} {h}x{wd}" + (" +res" if residual is not None else ""))
-    return orig_conv(x, w, bias, k, stride, act, out=out, residual=residual, cout=cout, cin=cin, impl=impl, kw=kw)
+    names.append(f"conv {cin or c:4d}->{cout or w.shape[0]:4d} k{k}s{stride} {h}x{wd}" + (" +res" if residual is not None else "")
+                 + (" +1x1" if chain is not None else ""))
+    return orig_conv(x, w, bias, k, stride, act, out=out, residual=residual, cout=cout, cin=cin, impl=impl, kw=kw, chain=chain,
+                     skip_out=skip_out)
 
 
 def gemm_wrap(a, w, bias, act=0, out=None, residual=None, out_dtype=torch.bfloat16, n=None, impl="tcgen05"):
@@ -94,6 +97,9 @@ def ideal_us(nm):
         ho, wo = (h + st - 1) // st, (w + st - 1) // st
         fl = 2.0 * B * ho * wo * cout * cin * k * k
         by = 2.0 * (B * h * w * cin + B * ho * wo * cout * (2 if "+res" in nm else 1) + cout * cin * k * k)
+        if "+1x1" in nm:                     # chained cout -> cout 1x1: its FLOPs, its output and its weights
+            fl += 2.0 * B * ho * wo * cout * cout
+            by += 2.0 * (B * ho * wo * cout + cout * cout)
     else:
         m = re.match(r"gemm M(\d+) K\s*(\d+) N\s*(\d+)", nm)
         mm, kk, nn = map(int, m.groups())
