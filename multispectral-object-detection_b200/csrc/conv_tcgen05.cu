@@ -73,7 +73,6 @@ struct ConvParams {
   int stage_c;              // bytes per epilogue staging buffer (8 KiB: one bf16 32-column chunk, 16 KiB: two / one f32)
   unsigned long long* span;    // debug (cft_debug_conv_spans): {min CTA start, max CTA end} of this launch in %globaltimer ns
   unsigned long long* trace;   // debug timeline (cft_debug_conv_trace): kTraceSlots clock samples per CTA, else null
-  int dbg_skip_store;       // timing experiments only (CFT_DEBUG_SKIP_STORE): do not issue the output TMA stores
   // chain mode (back-to-back GEMM): y2 = act2(W2 . y + bias2) per pixel, computed from the finished bf16 output tile while
   // it sits in the TMA-store staging buffer (= a K-major SWIZZLE_128B UMMA operand) -- a Bottleneck's cv1 fused into the conv
   // that produces its input (models/common.py:99-109).  Cout in {64, 128}, one n-block, W2 = [Cout, Cout] resident in smem.
@@ -794,7 +793,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(bar_id, 128);
-        if (gtid == 0 && !p.dbg_skip_store) {
+        if (gtid == 0) {
           for (int i = 0; i < nch; ++i)   // OOB pixels / channels are clipped by the tensor map
             tma_store_4d(&maps.c, stage_c + i * c_chunk_stride, t.n0 + (cg + col_groups * (sg + i)) * 32, t.x0, t.y0, t.b);
           bulk_commit();
@@ -912,17 +911,13 @@ bool g_attr_set = false;
 // CFT_CONV_CTAS=1 forces single-CTA tiles, =2 forces CTA pairs wherever legal (tests); unset = heuristic.
 const bool g_silu_tanh = getenv("CFT_SILU_EXP2") == nullptr;   // default: one-SFU-op SiLU; CFT_SILU_EXP2=1 -> ex2+rcp form
 const bool g_gelu_fast = getenv("CFT_GELU_ERFF") == nullptr;   // default: 2-SFU-op erf-GELU; CFT_GELU_ERFF=1 -> erff
-const bool g_one_team = getenv("CFT_ONE_TEAM") != nullptr;   // experiment: single epilogue team for single-wave launches
-const bool g_acc2 = getenv("CFT_ACC2") != nullptr;   // debug: always 2 accumulator buffers
 unsigned long long* g_trace_buf = nullptr;   // cft_debug_conv_trace
 unsigned long long* g_span_buf = nullptr;    // cft_debug_conv_spans
 int g_span_next = 0, g_span_max = 0;
 thread_local cft_conv_plan* g_plan_out = nullptr;   // cft_debug_conv_plan: report the plan instead of launching
 const bool g_no_bres = getenv("CFT_NO_BRES") != nullptr;     // debug: never keep the weights resident
-const bool g_stage8k = getenv("CFT_STAGE8K") != nullptr;     // experiment: 8 KiB staging buffers for every bf16 output
 const bool g_no_pdl = getenv("CFT_NO_PDL") != nullptr;
 const bool g_no_halo = getenv("CFT_NO_ROW_REUSE") != nullptr;
-const int g_ups_off = getenv("CFT_NO_TAP_GROUPING") != nullptr;
 const int g_force_ctas = getenv("CFT_CONV_CTAS") ? atoi(getenv("CFT_CONV_CTAS")) : 0;
 
 }  // namespace
@@ -979,13 +974,29 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.taps = a->k * kw;
   p.kw = kw;
   p.kelems = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
+  // yolov5x widths: Cin = 80 / 160 leave a 16 / 32-element tail that a 64-wide last chunk pads with zeros (38 % / 17 % of
+  // the MMA work); 32-wide chunks (SWIZZLE_64B rows) fit 160 exactly and 80 in 96.  CFT_KTAIL32=1 selects them (A/B pending)
+  static const bool ktail32 = getenv("CFT_KTAIL32") != nullptr;
+  if (ktail32 && a->Cin > 64 && a->Cin % 64 != 0 && a->Cin % 64 <= 32) p.kelems = 32;
   p.layout = p.kelems == 64 ? 2 : (p.kelems == 32 ? 4 : 6);   // UMMA LayoutType: SW128 / SW64 / SW32
   p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
-  p.ups = (p.kchunks == 1 && p.taps > 1 && !g_ups_off) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
+  p.ups = (p.kchunks == 1 && p.taps > 1) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
   p.stride = s;
   // row-reuse mode for L2-bound 3x3 stride-1 layers (measured L2->SM ceiling ~60 B/cycle/SM): 8 x 16 pixel tiles,
   // the 3 vertical taps share one (16+2) x 8 pixel box -> 2.7x less activation traffic than 9 separate boxes
   p.halo = (!g_no_halo && a->k == 3 && s == 1 && p.Wo % 8 == 0 && p.Ho % 16 == 0) ? 1 : 0;
+  if (p.halo) {
+    // a row-reuse stage = (TH + 2) x TW pixels + three weight taps of the n-block: wide layers (e.g. 256 -> 256 at 64 x 80,
+    // BASELINE config 3) would get a ring of fewer than 3 stages -- they take the plain path (one tap per stage, >= 4 stages)
+    const int kel = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
+    const int kch = (a->Cin + kel - 1) / kel;
+    const int ups_h = (kch == 1) ? 64 / kel : 1;
+    const int bn = pick_block_n(a->Cout);
+    const int a_sl = ((ups_h * 18 * 8 * kel * 2 + 1023) / 1024) * 1024;
+    const int b_sl = ((ups_h * 3 * (bn / 2) * kel * 2 + 1023) / 1024) * 1024;      // optimistic: a CTA pair halves it
+    const int resident = kw * kch * 3 * bn * kel * 2 <= 96 * 1024 && (a->Cout + bn - 1) / bn == 1;
+    if (!resident && (kSmemTotal - 1024 - kTailBytes - 4 * kStageCBytes) / (a_sl + b_sl) < 3) p.halo = 0;
+  }
   if (p.halo) {
     p.TW = 8;
     p.TH = 16;
@@ -1001,7 +1012,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
          p.block_n >= 128 && (p.block_n / 2) % 32 == 0 && a->Cout % (p.block_n / 2) == 0)
     p.block_n /= 2;
   p.n_blocks = (a->Cout + p.block_n - 1) / p.block_n;
-  p.acc_stages = (p.block_n <= 128 && !g_acc2 && !chain) ? 4 : 2;
+  p.acc_stages = (p.block_n <= 128 && !chain) ? 4 : 2;
   p.acc_cols = chain ? 128 : 512 / p.acc_stages;      // chain mode: main 2 x 128 columns, second accumulators at 256 + 128 t
   CFT_REQUIRE(m_tiles * p.n_blocks < (1LL << 31), "cft_conv2d: too many tiles");
   p.m_tiles = static_cast<int>(m_tiles);
@@ -1022,19 +1033,13 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     p.mg_tx = magic(p.tiles_x);
     p.mg_ty = magic(p.tiles_y);
   }
-  p.dbg_skip_store = getenv("CFT_DEBUG_SKIP_STORE") != nullptr;
   p.trace = g_trace_buf;
   p.span = nullptr;
   if (g_span_buf != nullptr && g_span_next < g_span_max) p.span = g_span_buf + 2 * (g_span_next++);
   p.out_f32 = a->out_dtype == CFT_DT_F32;
   // epilogue staging: a 32-column chunk is 128 rows x 64 B (bf16) or x 128 B (f32); column groups that own a single
   // bf16 chunk per tile get 8 KiB buffers, which leaves 32 KiB more for the operand ring
-  // one epilogue team when no CTA gets more than one tile (the small GEMMs of the CFT blocks, the P4/P5 1x1 convs at
-  // small batch): the tail after the last MMA is then one tile drained by 16 warps instead of 8
-  {
-    const int units0 = sm_count() / ctas;
-    p.teams = (g_one_team && !chain && p.num_tiles <= units0) ? 1 : kEpiTeams;
-  }
+  p.teams = kEpiTeams;
   p.chain = chain ? 1 : 0;
   p.k2chunks = chain ? a->Cout / 64 : 0;
   p.act2 = (a->act2 == CFT_ACT_SILU && g_silu_tanh) ? 3 : a->act2;
@@ -1043,7 +1048,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.w2_bytes = chain ? (a->Cout / ctas) * a->Cout * 2 : 0;         // [Cout / ctas rows][Cout] bf16, a multiple of 1 KiB
   const int col_groups_h = kEpiGroups / p.teams;
   const int chunks_per_group = ((p.block_n + 31) / 32 + col_groups_h - 1) / col_groups_h;
-  p.stage_c = (!p.out_f32 && (chunks_per_group <= 1 || g_stage8k)) ? 8 * 1024 : kStageCBytes;
+  p.stage_c = (!p.out_f32 && chunks_per_group <= 1) ? 8 * 1024 : kStageCBytes;
   if (chain) p.stage_c = a->Cout * 128;           // 4 x stage_c = the two teams' [128 px x Cout] bf16 tiles (2 x 16 / 32 KiB)
   const int ring_budget = kSmemTotal - 1024 - kTailBytes - kEpiGroups * p.stage_c - p.w2_bytes;
   p.a_slot = p.halo ? ((p.ups * (p.TH + 2) * p.TW * p.kelems * 2 + 1023) / 1024) * 1024 : kATileBytes;

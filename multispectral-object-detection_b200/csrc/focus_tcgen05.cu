@@ -52,7 +52,6 @@ struct FocusParams {
   int tiles_x, tiles_y, num_tiles;
   int act;              // CFT_ACT_NONE / CFT_ACT_SILU
   int chunks;           // ceil(Cout / 32)
-  int dbg;              // timing experiments only (CFT_FOCUS_DEBUG): 1 = builders idle, 2 = epilogue idle, 4 = no MMA
   int patches;          // image-patch ring depth (<= kFMaxPatches)
   int a_stages;         // A-tile ring depth (3, or 2 when the weights / staging of a wide layer need the room)
   const float* bias;
@@ -168,7 +167,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 128);
         const uint32_t a_lo = a_lo0 + stage * (kFATileBytes >> 4);
 #pragma unroll
-        for (int s = 0; s < ((p.dbg & 4) ? 1 : 9); ++s) {            // K steps of 16: atoms 0, 1 hold four each, atom 2 the last one
+        for (int s = 0; s < 9; ++s) {            // K steps of 16: atoms 0, 1 hold four each, atom 2 the last one
           const uint32_t atom = s >> 2, k = s & 3;
           const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + atom * (kFAtomBytes >> 4) + 2 * k);
           const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (w_lo0 + atom * w_atom16 + 2 * k);
@@ -208,7 +207,6 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       mbar_wait(&pfull[slot], pphase);
       const uint8_t* patch = smem_p + slot * kFPatchSlot;
       uint8_t* a_tile = smem_a + stage * kFATileBytes;
-      if (!(p.dbg & 1))
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -266,7 +264,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * 128);
-      for (int ch = cg; ch < ((p.dbg & 2) ? 0 : p.chunks); ch += 2) {
+      for (int ch = cg; ch < p.chunks; ch += 2) {
         uint32_t v[32];
         tmem_ld32(t_row + static_cast<uint32_t>(ch * 32), v);
         float f[32];
@@ -301,7 +299,7 @@ cft_focus_tcgen05_kernel(const __grid_constant__ FocusMaps maps, const __grid_co
       fence_proxy_async();
       __syncwarp();
       // every warp stores its own 32 accumulator rows = two 16-pixel rows of the tile: no cross-warp barrier in the loop
-      if (lane == 0 && !(p.dbg & 2)) {
+      if (lane == 0) {
         for (int ch = cg; ch < p.chunks; ch += 2)
           tma_store_4d(&maps.c, stage_c + ch * kFStageC + q * 2048, ch * 32, x0, y0 + 2 * q, b);
         bulk_commit();
@@ -381,7 +379,6 @@ extern "C" int cft_focus_conv(const void* img, int B, int H, int W, long long ba
   p.act = act;
   p.chunks = (Cout + 31) / 32;
   p.bias = bias;
-  p.dbg = getenv("CFT_FOCUS_DEBUG") ? atoi(getenv("CFT_FOCUS_DEBUG")) : 0;
 
   FocusMaps maps;
   int rc;

@@ -44,11 +44,6 @@ int check_cuda(cudaError_t e, const char* what) {
   return CFT_E_CUDA;
 }
 
-bool pdl_all() {
-  static const bool on = getenv("CFT_PDL_ALL") != nullptr;
-  return on;
-}
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {
