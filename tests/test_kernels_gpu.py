@@ -51,6 +51,7 @@ CONV_CASES = [
     (1, 256, 512, 40, 40, 3, 2, 1, False),      # n_blocks = 2
     (3, 32, 32, 24, 40, 1, 1, 1, False),        # Cin < 64 (yolov5s), OOB K fill
     (1, 80, 160, 16, 16, 3, 1, 1, True),        # yolov5x widths: K tail 80 = 64 + 16, N = 160
+    (2, 160, 160, 20, 20, 3, 1, 1, True),       # yolov5x: K = 160 = 2 x 64 + 32 per tap
     (1, 16, 64, 64, 64, 3, 1, 1, False),        # Focus-style 16-channel input
     (1, 512, 24, 20, 20, 1, 1, 0, False),       # Detect-style N = 24
     (2, 1024, 1024, 8, 8, 1, 1, 1, False),      # 16 k-chunks, 4 n-blocks
