@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFT_ABI_VERSION 6
+#define CFT_ABI_VERSION 7
 
 enum {
   CFT_OK = 0,
@@ -235,7 +235,7 @@ int cft_debug_conv_spans(void* buf, int max_launches);
  * yolov5{s,l,x}-x3 graphs through it (tests/test_conv_plan_cpu.py). */
 typedef struct cft_conv_plan {
   int ctas;                 /* 1, or 2 = CTA pairs (cta_group::2, UMMA M = 256)                         */
-  int TW, TH;               /* output-pixel tile of one CTA (TW * TH <= 128)                              */
+  int TW, TH;               /* output-pixel tile of one CTA (TW * TH * TB <= 128)                         */
   int Ho, Wo, tiles_x, tiles_y, m_tiles;
   int block_n, n_blocks;    /* N tile and their number (n_blocks * block_n >= Cout)                        */
   int num_tiles;            /* work items (pairs of m-tiles with ctas == 2) x n-blocks                     */
@@ -246,6 +246,7 @@ typedef struct cft_conv_plan {
   int teams, stage_c;       /* epilogue teams, bytes per epilogue staging buffer                           */
   int smem_bytes;           /* dynamic shared memory of the launch                                          */
   int grid;                 /* CTAs launched                                                               */
+  int TB;                   /* images per tile: the tile is TW x TH pixels of TB consecutive images, <= 128 px */
 } cft_conv_plan;
 int cft_debug_conv_plan(const cft_conv_args* a, cft_conv_plan* plan);
 

@@ -41,7 +41,7 @@ class ConvPlan(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "ctas", "TW", "TH", "Ho", "Wo", "tiles_x", "tiles_y", "m_tiles", "block_n", "n_blocks", "num_tiles",
         "kelems", "kchunks", "ups", "halo", "stages", "a_slot", "b_slot", "b_res", "acc_stages", "acc_cols",
-        "teams", "stage_c", "smem_bytes", "grid")]
+        "teams", "stage_c", "smem_bytes", "grid", "TB")]
 
 
 class GptBlockArgs(C.Structure):

@@ -79,6 +79,7 @@ struct ConvParams {
   int chain, k2chunks, act2, store_main, w2_bytes;
   const float* bias2;
   int TW, TH, tiles_x, tiles_y;
+  int TB, tile_px;         // images per tile (3-D tiles: TW x TH pixels of TB consecutive images); TW * TH * TB <= 128
   int n_blocks, block_n, num_tiles, stages;
   uint32_t mg_nb, mg_tx, mg_ty;   // ceil(2^32 / d) for n_blocks, tiles_x, tiles_y (0 = divide)
   int m_tiles;              // spatial tiles = B * tiles_y * tiles_x; num_tiles counts (pairs of) m-tiles x n-blocks
@@ -116,8 +117,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int work, 
   }
   const int mq = fast_div(m, p.tiles_x, p.mg_tx);
   const int tx = m - mq * p.tiles_x;
-  t.b = fast_div(mq, p.tiles_y, p.mg_ty);
-  const int ty = mq - t.b * p.tiles_y;
+  const int bq = fast_div(mq, p.tiles_y, p.mg_ty);
+  const int ty = mq - bq * p.tiles_y;
+  t.b = bq * p.TB;
   t.y0 = ty * p.TH;
   t.x0 = tx * p.TW;
   return t;
@@ -279,7 +281,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     int stage = 0;
     uint32_t phase = 0;
     long long p_wait = 0, pc0 = 0;      // debug trace: cycles the producer waited for free ring slots (row-reuse path)
-    const uint32_t tx_unit = static_cast<uint32_t>(p.TW * p.TH + b_rows) * row_bytes;   // per CTA, per unit
+    const uint32_t tx_unit = static_cast<uint32_t>(p.tile_px + b_rows) * row_bytes;   // per CTA, per unit
     for (int tile = work0; tile < p.num_tiles; tile += work_stride) {
       const TileCoord t = decode_tile<kCtas>(p, tile, rank);
       auto tap_offsets = [&](int tap, int& mi, int& dy, int& dx) {
@@ -572,7 +574,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
     const int cps = p.out_f32 ? 1 : (p.stage_c >> 13);               // chunks per staging buffer (8 / 16 KiB)
     const uint32_t c_row_bytes = p.out_f32 ? 128u : 64u;             // one 32-channel row in the staging box
     const uint32_t c_chunk_stride = 128u * c_row_bytes;
-    const uint32_t c_box_bytes = static_cast<uint32_t>(p.TW * p.TH) * c_row_bytes;
+    const uint32_t c_box_bytes = static_cast<uint32_t>(p.tile_px) * c_row_bytes;
     const bool use_res = p.res != nullptr;
     int bias_n0 = -1;
     const int bar_id = 1 + grp;
@@ -589,7 +591,7 @@ cft_conv_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_co
       uint8_t* A2 = smem_c + team * (n64 * 16384);
       float* bias2_t = bias2_s + team * 128;
       uint64_t* rb = &res_bar[team];
-      const uint32_t box_bytes = static_cast<uint32_t>(p.TW * p.TH) * 128u;
+      const uint32_t box_bytes = static_cast<uint32_t>(p.tile_px) * 128u;
       const int nch = p.Cout >> 5;                       // 32-column chunks; this column group: cg, cg + 2
       const int tbar = 8 + team;
       const uint32_t lane_q = static_cast<uint32_t>(q * 32) << 16;
@@ -887,24 +889,34 @@ int pick_block_n(int cout) {
   return 256;
 }
 
-void pick_spatial_tile(int Ho, int Wo, int* TW, int* TH) {
+const bool g_no_tile3d = getenv("CFT_NO_BATCH_TILES") != nullptr;     // tiles never span images (A/B of the 3-D tiles)
+// The output-pixel tile of one CTA: TW x TH pixels of TB consecutive images, TW * TH * TB <= 128 (one UMMA M tile; the TMA
+// boxes are (channels, TW, TH, TB) of the (C, W, H, B) tensors, so image borders zero-fill per image).  40 x 40 and 20 x 20
+// maps have no 2-D tile of 128 pixels without waste (best: 40 x 3 = 120 of 128 rows, 14 tiles per image instead of 12.5);
+// 8 x 8 x 2 images / 4 x 4 x 8 images are exact -- 11 % / 22 % fewer tiles and, at batch 32, 3 instead of 4 waves of the
+// N = 256 pair tiles of the P4 Bottlenecks.
+void pick_spatial_tile(int Ho, int Wo, int B, int* TW, int* TH, int* TB) {
   long best = -1;
-  int bw = 1, bh = 1;
+  int bw = 1, bh = 1, bb = 1;
   for (int tw = 1; tw <= 128 && tw <= Wo; ++tw) {
-    int th = 128 / tw;
-    if (th > Ho) th = Ho;
-    if (th < 1) continue;
-    const long tiles = static_cast<long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
-    // fewest tiles first, then the widest rows (longer contiguous runs per TMA box row)
-    const long score = tiles * 1024 - tw;
-    if (best < 0 || score < best) {
-      best = score;
-      bw = tw;
-      bh = th;
+    for (int th = 1; th * tw <= 128 && th <= Ho; ++th) {
+      int tb = 128 / (tw * th);
+      if (tb > B) tb = B;
+      if (g_no_tile3d) tb = 1;
+      const long tiles = static_cast<long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((B + tb - 1) / tb);
+      // fewest tiles first, then the fewest images per tile, then the widest rows (longer contiguous runs per TMA box row)
+      const long score = (tiles * 256 + tb) * 256 - tw;
+      if (best < 0 || score < best) {
+        best = score;
+        bw = tw;
+        bh = th;
+        bb = tb;
+      }
     }
   }
   *TW = bw;
   *TH = bh;
+  *TB = bb;
 }
 
 bool g_attr_set = false;
@@ -974,10 +986,6 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
   p.taps = a->k * kw;
   p.kw = kw;
   p.kelems = a->Cin <= 16 ? 16 : (a->Cin <= 32 ? 32 : 64);
-  // yolov5x widths: Cin = 80 / 160 leave a 16 / 32-element tail that a 64-wide last chunk pads with zeros (38 % / 17 % of
-  // the MMA work); 32-wide chunks (SWIZZLE_64B rows) fit 160 exactly and 80 in 96.  CFT_KTAIL32=1 selects them (A/B pending)
-  static const bool ktail32 = getenv("CFT_KTAIL32") != nullptr;
-  if (ktail32 && a->Cin > 64 && a->Cin % 64 != 0 && a->Cin % 64 <= 32) p.kelems = 32;
   p.layout = p.kelems == 64 ? 2 : (p.kelems == 32 ? 4 : 6);   // UMMA LayoutType: SW128 / SW64 / SW32
   p.kchunks = (a->Cin + p.kelems - 1) / p.kelems;
   p.ups = (p.kchunks == 1 && p.taps > 1) ? 64 / p.kelems : 1;   // small-Cin convs: several taps per stage
@@ -997,16 +1005,18 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     const int resident = kw * kch * 3 * bn * kel * 2 <= 96 * 1024 && (a->Cout + bn - 1) / bn == 1;
     if (!resident && (kSmemTotal - 1024 - kTailBytes - 4 * kStageCBytes) / (a_sl + b_sl) < 3) p.halo = 0;
   }
+  p.TB = 1;
   if (p.halo) {
     p.TW = 8;
     p.TH = 16;
   } else {
-    pick_spatial_tile(p.Ho, p.Wo, &p.TW, &p.TH);
+    pick_spatial_tile(p.Ho, p.Wo, p.B, &p.TW, &p.TH, &p.TB);
   }
+  p.tile_px = p.TW * p.TH * p.TB;
   p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
   p.block_n = pick_block_n(a->Cout);
-  const long long m_tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y;
+  const long long m_tiles = static_cast<long long>((p.B + p.TB - 1) / p.TB) * p.tiles_x * p.tiles_y;
   // too few tiles to fill the GPU (the M = 4096 GEMMs of the CFT blocks): trade tile width for parallelism
   while (a->Cin * p.taps <= 1024 && 2 * m_tiles * ((a->Cout + p.block_n - 1) / p.block_n) <= sm_count() &&
          p.block_n >= 128 && (p.block_n / 2) % 32 == 0 && a->Cout % (p.block_n / 2) == 0)
@@ -1080,7 +1090,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
 
   if (g_plan_out != nullptr) {      // planning only (host tests): everything below needs the driver / a device
     cft_conv_plan* o = g_plan_out;
-    o->ctas = ctas; o->TW = p.TW; o->TH = p.TH; o->Ho = p.Ho; o->Wo = p.Wo;
+    o->ctas = ctas; o->TW = p.TW; o->TH = p.TH; o->TB = p.TB; o->Ho = p.Ho; o->Wo = p.Wo;
     o->tiles_x = p.tiles_x; o->tiles_y = p.tiles_y; o->m_tiles = p.m_tiles;
     o->block_n = p.block_n; o->n_blocks = p.n_blocks; o->num_tiles = p.num_tiles;
     o->kelems = p.kelems; o->kchunks = p.kchunks; o->ups = p.ups; o->halo = p.halo;
@@ -1103,7 +1113,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->B};
     cuuint64_t str[3] = {(cuuint64_t)a->ldx * eb, (cuuint64_t)a->W * a->ldx * eb,
                          (cuuint64_t)a->H * a->W * a->ldx * eb};
-    cuuint32_t box[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
     rc = encode_map(&maps.a[0], xb, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
     if (rc) return rc;
     maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
@@ -1118,7 +1128,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
         cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)(a->W / 2), (cuuint64_t)(a->H / 2), (cuuint64_t)a->B};
         cuuint64_t str[3] = {(cuuint64_t)2 * a->ldx * eb, (cuuint64_t)2 * a->W * a->ldx * eb,
                              (cuuint64_t)a->H * a->W * a->ldx * eb};
-        cuuint32_t box[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)p.kelems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
         const __nv_bfloat16* base = xb + (static_cast<size_t>(py) * a->W + px) * a->ldx;
         rc = encode_map(&maps.a[py * 2 + px], base, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, op_swz);
         if (rc) return rc;
@@ -1138,7 +1148,7 @@ extern "C" int cft_conv2d(const cft_conv_args* a, void* stream_v) {
     const uint8_t* yb = reinterpret_cast<const uint8_t*>(a->y) + static_cast<size_t>(a->y_coff) * es;
     cuuint64_t dims[4] = {(cuuint64_t)a->Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)a->B};
     cuuint64_t str[3] = {(cuuint64_t)a->ldy * es, (cuuint64_t)p.Wo * a->ldy * es, (cuuint64_t)p.Ho * p.Wo * a->ldy * es};
-    cuuint32_t box[4] = {chain ? 64u : 32u, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t box[4] = {chain ? 64u : 32u, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
     const CUtensorMapSwizzle c_swz = (p.out_f32 || chain) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     rc = encode_map(&maps.c, yb, 4, dims, str, box,
                     p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c_swz);

@@ -291,6 +291,21 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
   bilin(y, a.va, a.H, &y0, &y1, &ly);
   const int c_base = cc * kUnpoolCC;
   const int cw = min(kUnpoolCC, a.C - c_base);    // channels in this chunk (multiple of 8)
+  const int cv8 = cw / 8;
+  const int items = a.W * cv8;
+  const long long row_pix = (static_cast<long long>(b) * a.H + y) * a.W;
+  // the thread's first (pixel, 8-channel) item: its two activation vectors do not depend on the token rows, so their HBM
+  // loads are issued BEFORE the blend of the token rows (L2 latency + a barrier) instead of after it
+  bf16x8 pre_r, pre_i;
+  pre_r.u = make_uint4(0, 0, 0, 0);
+  pre_i.u = make_uint4(0, 0, 0, 0);
+  if (static_cast<int>(threadIdx.x) < items) {
+    const int cv = threadIdx.x % cv8, x = threadIdx.x / cv8;
+    const long long pix = row_pix + x;
+    const int c = c_base + cv * 8;
+    if (a.x_rgb) pre_r = *reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c);
+    if (a.x_ir) pre_i = *reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c);
+  }
   for (int i = threadIdx.x; i < 2 * a.ha * (cw / 4); i += blockDim.x) {
     const int c4 = i % (cw / 4);
     const int t = i / (cw / 4);                   // m * ha + tx
@@ -306,15 +321,17 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
     *reinterpret_cast<float4*>(srow + t * kUnpoolCC + c4 * 4) = r;
   }
   __syncthreads();
-  const int cv8 = cw / 8;
-  const long long row_pix = (static_cast<long long>(b) * a.H + y) * a.W;
-  for (int i = threadIdx.x; i < a.W * cv8; i += blockDim.x) {
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int cv = i % cv8, x = i / cv8;
     int x0, x1;
     float lx;
     bilin(x, a.ha, a.W, &x0, &x1, &lx);
     const long long pix = row_pix + x;
     const int c = c_base + cv * 8;
+    if (i != static_cast<int>(threadIdx.x)) {     // later passes (rows wider than the block): plain loads
+      if (a.x_rgb) pre_r = *reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c);
+      if (a.x_ir) pre_i = *reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c);
+    }
     float r[2][8];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
@@ -325,13 +342,13 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
     }
     if (a.x_rgb) {
       float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c), f);
+      unpack8(pre_r, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[0][j] += f[j];
     }
     if (a.x_ir) {
       float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c), f);
+      unpack8(pre_i, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[1][j] += f[j];
     }

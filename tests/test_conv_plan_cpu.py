@@ -38,8 +38,11 @@ def _check(p, B, H, W, cin, cout, k, s, what, min_stages=2):
         assert (p.Ho, p.Wo) == (ho, wo), what
         assert p.tiles_x * p.TW >= wo and p.tiles_y * p.TH >= ho, what   # tiles cover the output
         assert (p.tiles_x - 1) * p.TW < wo and (p.tiles_y - 1) * p.TH < ho, what
-        assert p.m_tiles == B * p.tiles_x * p.tiles_y, what
-    assert 1 <= p.TW * p.TH <= 128, what                                # one UMMA M tile
+        assert p.TB >= 1 and p.m_tiles == -(-B // p.TB) * p.tiles_x * p.tiles_y, what   # TB consecutive images per tile
+        assert p.m_tiles <= B * -(-wo // min(wo, 128)) * -(-ho // max(1, min(ho, 128 // min(wo, 128)))), what   # never worse than rows
+        if p.halo:
+            assert p.TB == 1, what
+    assert 1 <= p.TW * p.TH * p.TB <= 128, what                         # one UMMA M tile
     assert p.block_n % 16 == 0 and 16 <= p.block_n <= 256, what         # UMMA N constraint (M = 128)
     assert p.n_blocks * p.block_n >= cout and (p.n_blocks - 1) * p.block_n < cout, what
     assert p.ctas in (1, 2), what
@@ -141,3 +144,17 @@ def test_plan_rejects_bad_arguments(cft):
     a.k, a.stride = 1, 2
     assert lib.cft_debug_conv_plan(C.byref(a), C.byref(p)) == 1        # stride 2 only for 3x3
     assert lib.cft_debug_conv_plan(C.byref(a), None) == 1
+
+
+def test_batch_spanning_tiles_are_exact_on_40x40_and_20x20(cft):
+    """40 x 40 and 20 x 20 maps have no waste-free 2-D tile of 128 pixels; tiles of 8 x 8 x 2 images / 4 x 4 x 8 images
+    (or any other exact (TW, TH, TB)) fill every UMMA row: batch 32 -> 400 / 100 tiles instead of 448 / 128."""
+    for (H, W, cin, cout, s, want) in [(40, 40, 256, 256, 1, 400), (20, 20, 512, 512, 1, 100), (80, 80, 256, 512, 2, 400),
+                                       (40, 40, 512, 1024, 2, 100)]:
+        p = _plan(cft, 32, H, W, cin, cout, 3, s)
+        assert p.m_tiles == want and p.TW * p.TH * p.TB == 128, (H, W, p.TW, p.TH, p.TB, p.m_tiles)
+        _check(p, 32, H, W, cin, cout, 3, s, f"{H}x{W}")
+    p = _plan(cft, 1, 40, 40, 256, 256, 3, 1)                # batch 1: nothing to span
+    assert p.TB == 1 and p.m_tiles == 14
+    p = _plan(cft, 3, 20, 20, 512, 512, 3, 1)                # ragged batch: 3 images in one 4 x 8 x 3 ... tile set
+    assert p.TW * p.TH * p.TB <= 128 and p.m_tiles <= 12

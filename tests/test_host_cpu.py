@@ -60,7 +60,7 @@ def test_c_abi_exports_every_declared_symbol(cft):
     for name in declared:
         assert hasattr(lib, name), f"libcft_b200.so does not export {name}"
     assert set(cft._lib.SIGNATURES) == declared
-    assert lib.cft_abi_version() == 6
+    assert lib.cft_abi_version() == 7
 
 
 def test_forward_fails_loudly_without_cuda(cft):

@@ -60,6 +60,11 @@ CONV_CASES = [
     (2, 16, 32, 32, 32, 3, 2, 1, False),        # 32 B operand rows (SWIZZLE_32B ring), stride 2
     (1, 64, 96, 20, 20, 3, 1, 1, True),         # 3 column chunks: uneven split over the 2 epilogue groups
     (32, 128, 128, 80, 80, 3, 1, 1, True),      # full-size C3 bottleneck conv (batch 32): many tiles per CTA
+    (4, 128, 128, 40, 40, 3, 1, 1, True),       # batch-spanning tiles: 8 x 8 px x 2 images, residual through the same boxes
+    (8, 64, 128, 20, 20, 3, 1, 1, False),       # 4 x 4 px x 8 images
+    (3, 64, 64, 20, 20, 3, 1, 1, True),         # ragged: 3 images in tiles of up to 8 (out-of-range images clipped / zero-filled)
+    (5, 64, 128, 40, 40, 3, 2, 1, False),       # stride 2 -> 20 x 20 output, 5 images over 4 x 4 x 8 tiles
+    (6, 256, 256, 40, 40, 3, 1, 1, True),       # CTA pairs over batch-spanning tiles, N = 256
 ]
 
 
@@ -292,6 +297,7 @@ CHAIN_CASES = [
     (8, 128, 80, 80, 3, 1, True, False),       # 800 tiles: both teams, many tiles per CTA, accumulator / staging reuse
     (8, 64, 160, 160, 3, 1, True, False),      # the yolov5l P2 Bottleneck shape at batch 8
     (5, 128, 32, 24, 3, 2, False, False),      # stride-2 producer
+    (5, 128, 20, 20, 3, 1, True, False),       # batch-spanning tiles (4 x 4 px x 5 images), residual, chained 1x1
 ]
 
 

@@ -22,7 +22,7 @@ ARMS = [
     ({"CFT_CONV_CTAS": "1"}, KERNELS, "conv_tcgen05 or chained or gemm_linear"),   # never CTA pairs
     ({"CFT_CONV_CTAS": "2"}, KERNELS, "conv_tcgen05 or chained or gemm_linear"),   # CTA pairs wherever legal
     ({"CFT_ATTENTION_SIMT": "1"}, KERNELS, "attention_core"),              # the CUDA-core attention cross-check kernel
-    ({"CFT_KTAIL32": "1"}, KERNELS, "conv_tcgen05"),                       # 32-wide K chunks for 80 / 160-channel operands
+    ({"CFT_NO_BATCH_TILES": "1"}, KERNELS, "conv_tcgen05 or chained"),     # tiles never span images (the round-1 tiling)
     ({"CFT_NO_CONV_CHAIN": "1"}, MODEL, "golden"),                         # every Bottleneck 1x1 launched separately
     ({"CFT_NO_FUSED_BLOCK": "1"}, MODEL, "golden"),                        # CFT blocks on the per-op path
     ({"CFT_FUSED_BLOCK_MAX_D": "512"}, MODEL, "golden"),                   # ... and the one-launch kernel up to d = 512
