@@ -21,6 +21,7 @@ import logging
 import math
 import os
 from copy import deepcopy
+from fractions import Fraction
 from pathlib import Path
 from typing import Dict, List, Optional
 
@@ -217,19 +218,14 @@ class Model(nn.Module):
         return st
 
     def _slot(self, plan, bufs, i, ref, m=None):
-        """Channel-slice view of the Concat buffer that layer i's output is planned into."""
-        cat_i, c0, c1, ctot, scale = plan["slots"][i]
+        """Channel-slice view of the Concat buffer that layer i's output is planned into.  ``ref`` is the producer's (first)
+        input; its resolution times the producer's planned scale (``_plan_graph``: Focus / strided Conv shrink, Upsample
+        doubles) is the resolution of the buffer."""
+        cat_i, c0, c1, ctot, (mul, div) = plan["slots"][i]
         key = cat_i
         if key not in bufs:
-            b = ref.shape[0]
-            if m is not None and isinstance(m, M.Upsample):
-                h, w = ref.shape[2] * 2, ref.shape[3] * 2
-            elif m is not None and isinstance(m, M.Conv):
-                s = m.conv.stride[0]
-                h, w = (ref.shape[2] + s - 1) // s, (ref.shape[3] + s - 1) // s
-            else:
-                h, w = ref.shape[2], ref.shape[3]
-            bufs[key] = ops.empty_nhwc(b, ctot, h, w, ref.device)
+            h, w = (ref.shape[2] * mul + div - 1) // div, (ref.shape[3] * mul + div - 1) // div
+            bufs[key] = ops.empty_nhwc(ref.shape[0], ctot, h, w, ref.device)
         return M.concat_slot(bufs[key], c0, c1)
 
     # -------------------------------------------------------------------------------- misc API
@@ -281,8 +277,9 @@ def fuse_conv_and_bn(conv, bn):
 def _plan_graph(layers: nn.Sequential) -> dict:
     """Static analysis of the layer list.
 
-    slots[i] = (concat layer, c0, c1, c_total, _) when layer i's output can be written directly into
-    the buffer of a later Concat (i must be a single-tensor producer that accepts ``out=``);
+    slots[i] = (concat layer, c0, c1, c_total, (mul, div)) when layer i's output can be written directly into
+    the buffer of a later Concat (i must be a single-tensor producer that accepts ``out=``; its output is
+    ``ceil(input * mul / div)`` pixels high / wide; all producers of one Concat must sit at the same total stride);
     gpt_groups[g] = {rgb: Add2 idx, ir: Add2 idx, sum: Add idx} for every GPT whose two outputs are
     consumed only by an Add2 pair that is merged by one Add (the x3 pattern, yaml rows 10-12 + 29).
     """
@@ -340,6 +337,24 @@ def _plan_graph(layers: nn.Sequential) -> dict:
             continue
         gpt_groups[g] = {"rgb": rgb_l.i, "ir": ir_l.i, "sum": adds[0]}
 
+    # per-layer scale relative to the layer's own (first) input, and the total stride relative to the image
+    rel: Dict[int, tuple] = {}
+    total: Dict[int, Fraction] = {}
+    for m in layers:
+        if isinstance(m, M.Focus):
+            r = (1, 2)
+        elif isinstance(m, M.Conv):
+            r = (1, int(m.conv.stride[0]))
+        elif isinstance(m, M.Upsample):
+            r = (2, 1)
+        else:
+            r = (1, 1)
+        rel[m.i] = r
+        srcs = [m.f] if isinstance(m.f, int) else list(m.f)
+        first = srcs[0]
+        base = Fraction(1) if (first == -4 or (first == -1 and m.i == 0)) else total[(m.i - 1) if first == -1 else first]
+        total[m.i] = base * Fraction(r[1], r[0])
+
     writable = (M.Conv, M.C3, M.SPP, M.Focus, M.Upsample, M.Add, M.Add2)
     slots = {}
     for m in layers:
@@ -349,9 +364,10 @@ def _plan_graph(layers: nn.Sequential) -> dict:
         ctot = sum(out_ch[s] for s in srcs)
         c0 = 0
         ok = all(isinstance(layers[s], writable) and s not in slots for s in srcs) and len(set(srcs)) == len(srcs)
+        ok = ok and len({total[s] for s in srcs}) == 1          # else: plain Concat copies (and its own shape error)
         for s in srcs:
             if ok:
-                slots[s] = (m.i, c0, c0 + out_ch[s], ctot, 1)
+                slots[s] = (m.i, c0, c0 + out_ch[s], ctot, rel[s])
             c0 += out_ch[s]
     # Two-stream execution: the IR branch between two fusion points is a chain of single-input layers that does not
     # depend on the RGB chain listed just before it in the yaml (rows 5-9, 15-16, 23-25).  chains[first] = (last, src):

@@ -27,6 +27,15 @@ def conv_case(cin, cout, h, w, k, s, res=False, b=B):
     return lambda: ops.conv2d(x, wp, bp, k, s, 1, out=y, cout=cout, residual=r)
 
 
+def chain_case(c, h, w, b=B):
+    """3x3 c -> c (+ residual) with the next Bottleneck's 1x1 chained in its epilogue (chain mode)."""
+    x, r = nhwc(b, c, h, w), nhwc(b, c, h, w)
+    wp, bp = ops.pack_conv_weight(torch.randn(c, c, 3, 3) / math.sqrt(9 * c), torch.zeros(c), None, device=DEV)
+    w2, b2 = ops.pack_conv_weight(torch.randn(c, c, 1, 1) / math.sqrt(c), torch.zeros(c), None, device=DEV)
+    y, y2 = nhwc(b, c, h, w), nhwc(b, c, h, w)
+    return lambda: ops.conv2d(x, wp, bp, 3, 1, 1, out=y, cout=c, residual=r, chain=(w2, b2, 1, y2))
+
+
 def gemm_case(m, kdim, n, act=0, res32=False):
     a = torch.randn(m, kdim, device=DEV).to(torch.bfloat16)
     wp, bp = ops.pack_linear_weight(torch.randn(n, kdim) / math.sqrt(kdim), torch.zeros(n), device=DEV)
@@ -45,6 +54,8 @@ CASES = {
     # the tcgen05 implicit-GEMM kernel, one launch per shape class (SURVEY.md section 8d catalogue)
     "conv_c3_p3_3x3_128_rowreuse_pairs": lambda: conv_case(128, 128, 80, 80, 3, 1, res=True),
     "conv_c3_p4_3x3_256_pairs_n256": lambda: conv_case(256, 256, 40, 40, 3, 1, res=True),
+    "conv_c3_p5_3x3_512_tiles_4x4x8": lambda: conv_case(512, 512, 20, 20, 3, 1, res=True),
+    "conv_c3_p3_3x3_128_chain_1x1": lambda: chain_case(128, 80, 80),
     "conv_c3_p2_3x3_64_resident_weights": lambda: conv_case(64, 64, 160, 160, 3, 1, res=True),
     "conv_c3_p3_1x1_128_flat_hbm": lambda: conv_case(128, 128, 80, 80, 1, 1),
     "conv_down_p4_3x3s2_256_512": lambda: conv_case(256, 512, 80, 80, 3, 2),

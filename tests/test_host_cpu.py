@@ -50,6 +50,28 @@ def test_planner_finds_concat_slots_and_gpt_groups(cft):
     assert plan["slots"][33][:4] == (34, 0, 512, 1024) and plan["slots"][30][:4] == (34, 512, 1024, 1024)
     assert plan["slots"][32][:4] == (44, 512, 1024, 1024) and plan["slots"][36][:4] == (41, 256, 512, 512)
     assert sorted(set(model.save)) == [1, 4, 9, 10, 11, 12, 14, 16, 17, 18, 19, 22, 25, 26, 27, 28, 29, 30, 32, 36, 39, 42, 45]
+    # the producer's scale relative to its own input sizes the Concat buffer: Upsample doubles, Conv stride 2 halves
+    assert plan["slots"][33][4] == (2, 1) and plan["slots"][30][4] == (1, 1)
+    strided = [i for i, sl in plan["slots"].items() if sl[4] == (1, 2)]
+    assert strided and all(isinstance(model.model[i], cft.modules.Conv) and model.model[i].conv.stride[0] == 2 for i in strided)
+
+
+def test_planner_sizes_concat_buffers_from_the_stride_table(cft):
+    """A Focus (or any resolution-changing producer) writing into a Concat gets a buffer of its OUTPUT resolution; producers
+    at different total strides are not planned into one buffer (`_slot()` looked at Upsample / Conv only)."""
+    from importlib import import_module
+    model_mod = import_module(cft.__name__ + ".model")
+    M = cft.modules
+
+    def layer(m, i, f):
+        m.i, m.f = i, f
+        return m
+    import torch.nn as nn
+    layers = nn.Sequential(layer(M.Focus(3, 16, 3), 0, -1), layer(M.Focus(3, 16, 3), 1, -4), layer(M.Concat(1), 2, [0, 1]),
+                           layer(M.Conv(32, 32, 3, 2), 3, -1), layer(M.Concat(1), 4, [2, 3]))
+    plan = model_mod._plan_graph(layers)
+    assert plan["slots"][0] == (2, 0, 16, 32, (1, 2)) and plan["slots"][1] == (2, 16, 32, 32, (1, 2))
+    assert 3 not in plan["slots"] and 2 not in plan["slots"]          # stride 2 vs stride 4: never one buffer
 
 
 def test_c_abi_exports_every_declared_symbol(cft):
