@@ -63,12 +63,12 @@ pool_tokens_kernel(const __nv_bfloat16* __restrict__ rgb, int ld_rgb, const __nv
 }
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
-template <bool kOutF32>
+template <bool kOutF32, int kMaxV>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                  const float* __restrict__ be, float eps, long long rows, int C, void* __restrict__ y) {
   pdl_prologue();
-  // one warp per row; the row is read from global memory once and kept in registers (C <= 2048)
-  constexpr int kMaxV = 16;                       // float4 per lane (C <= 2048)
+  // one warp per row; the row is read from global memory once and kept in registers: kMaxV float4 per lane
+  // (C <= 128 kMaxV; 4 / 8 / 16 for C <= 512 / 1024 / 2048 -- 16 costs 98 registers = 16 resident warps per SM)
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -281,7 +281,8 @@ __global__ void unpool_kernel(UnpoolArgs a) {
 // then does only the horizontal lerp for its (pixel, 8-channel vector) -- the feature maps are streamed once,
 // coalesced, and the token tensor is read ~H/va times less often than by the per-pixel kernel.
 constexpr int kUnpoolCC = 64;
-__global__ void unpool_rows_kernel(UnpoolArgs a) {
+constexpr int kUnpoolMaxThreads = 640;   // x 2 CTAs per SM: <= 48 registers per thread (56 unbounded = ONE 640-thread CTA per SM)
+__global__ void __launch_bounds__(kUnpoolMaxThreads, 2) unpool_rows_kernel(UnpoolArgs a) {
   pdl_prologue();
   extern __shared__ float srow[];                 // [2][ha][kUnpoolCC]
   const int y = blockIdx.x, cc = blockIdx.y, b = blockIdx.z;
@@ -291,21 +292,6 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
   bilin(y, a.va, a.H, &y0, &y1, &ly);
   const int c_base = cc * kUnpoolCC;
   const int cw = min(kUnpoolCC, a.C - c_base);    // channels in this chunk (multiple of 8)
-  const int cv8 = cw / 8;
-  const int items = a.W * cv8;
-  const long long row_pix = (static_cast<long long>(b) * a.H + y) * a.W;
-  // the thread's first (pixel, 8-channel) item: its two activation vectors do not depend on the token rows, so their HBM
-  // loads are issued BEFORE the blend of the token rows (L2 latency + a barrier) instead of after it
-  bf16x8 pre_r, pre_i;
-  pre_r.u = make_uint4(0, 0, 0, 0);
-  pre_i.u = make_uint4(0, 0, 0, 0);
-  if (static_cast<int>(threadIdx.x) < items) {
-    const int cv = threadIdx.x % cv8, x = threadIdx.x / cv8;
-    const long long pix = row_pix + x;
-    const int c = c_base + cv * 8;
-    if (a.x_rgb) pre_r = *reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c);
-    if (a.x_ir) pre_i = *reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c);
-  }
   for (int i = threadIdx.x; i < 2 * a.ha * (cw / 4); i += blockDim.x) {
     const int c4 = i % (cw / 4);
     const int t = i / (cw / 4);                   // m * ha + tx
@@ -321,17 +307,15 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
     *reinterpret_cast<float4*>(srow + t * kUnpoolCC + c4 * 4) = r;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+  const int cv8 = cw / 8;
+  const long long row_pix = (static_cast<long long>(b) * a.H + y) * a.W;
+  for (int i = threadIdx.x; i < a.W * cv8; i += blockDim.x) {
     const int cv = i % cv8, x = i / cv8;
     int x0, x1;
     float lx;
     bilin(x, a.ha, a.W, &x0, &x1, &lx);
     const long long pix = row_pix + x;
     const int c = c_base + cv * 8;
-    if (i != static_cast<int>(threadIdx.x)) {     // later passes (rows wider than the block): plain loads
-      if (a.x_rgb) pre_r = *reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c);
-      if (a.x_ir) pre_i = *reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c);
-    }
     float r[2][8];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
@@ -342,13 +326,13 @@ __global__ void unpool_rows_kernel(UnpoolArgs a) {
     }
     if (a.x_rgb) {
       float f[8];
-      unpack8(pre_r, f);
+      unpack8(*reinterpret_cast<const bf16x8*>(a.x_rgb + pix * a.ld_xr + c), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[0][j] += f[j];
     }
     if (a.x_ir) {
       float f[8];
-      unpack8(pre_i, f);
+      unpack8(*reinterpret_cast<const bf16x8*>(a.x_ir + pix * a.ld_xi + c), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[1][j] += f[j];
     }
@@ -442,12 +426,18 @@ extern "C" int cft_layernorm(const float* x, const float* gamma, const float* be
   const int warps = 4;
   const long long blocks = (rows + warps - 1) / warps;
   LaunchScope ls(CFT_K_LAYERNORM, stream);
-  if (out_dtype == CFT_DT_F32)
-    cft::launch(layernorm_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream, x, gamma, beta, eps, rows, C, y);
-  else if (out_dtype == CFT_DT_BF16)
-    cft::launch(layernorm_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), 0, stream, x, gamma, beta, eps, rows, C, y);
-  else
-    return fail_arg("cft_layernorm: bad out_dtype");
+  if (out_dtype != CFT_DT_F32 && out_dtype != CFT_DT_BF16) return fail_arg("cft_layernorm: bad out_dtype");
+  const bool f32 = out_dtype == CFT_DT_F32;
+  const dim3 grid(static_cast<unsigned>(blocks)), block(warps * 32);
+#define CFT_LN_LAUNCH(V)                                                                                          \
+  do {                                                                                                            \
+    if (f32) cft::launch(layernorm_kernel<true, V>, grid, block, 0, stream, x, gamma, beta, eps, rows, C, y);     \
+    else cft::launch(layernorm_kernel<false, V>, grid, block, 0, stream, x, gamma, beta, eps, rows, C, y);        \
+  } while (0)
+  if (C <= 512) CFT_LN_LAUNCH(4);
+  else if (C <= 1024) CFT_LN_LAUNCH(8);
+  else CFT_LN_LAUNCH(16);
+#undef CFT_LN_LAUNCH
   return ls.finish("cft_layernorm launch");
 }
 
@@ -503,7 +493,7 @@ extern "C" int cft_gpt_unpool(const float* tok, int B, int H, int W, int C, int 
     // one (pixel, 8-channel vector) item per thread and pass: balance the passes (640 items = 1 pass of 640 threads, not
     // 512 + 128) so that no pass runs mostly empty
     const int items = W * (kUnpoolCC / 8);
-    const int passes = (items + 1023) / 1024;
+    const int passes = (items + kUnpoolMaxThreads - 1) / kUnpoolMaxThreads;
     int threads = ((items + passes - 1) / passes + 31) / 32 * 32;
     if (threads < 64) threads = 64;
     dim3 grid(H, chunks, B);

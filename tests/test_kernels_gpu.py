@@ -369,7 +369,7 @@ def test_gpt_pool_tokens(H, W, C, cft):
     assert (tok - ref).abs().max() <= 1e-5 * max(1.0, float(ref.abs().max())) + 1e-5
 
 
-@pytest.mark.parametrize("C", [128, 256, 1024, 1280])
+@pytest.mark.parametrize("C", [128, 256, 512, 640, 1024, 1280, 2048])
 def test_layernorm(C, cft):
     x = rnd(300, C, seed=1, scale=3.0).to(DEV) + 0.5
     g, b = (torch.rand(C) + 0.5).to(DEV), rnd(C, seed=2, scale=0.1).to(DEV)
