@@ -2,8 +2,10 @@
 //
 //   S = Q K^T      tcgen05.mma  128 x 128 x dk   (A = Q, B = K, both K-major smem tiles loaded by TMA
 //                                                 straight out of the fused QKV activation [B*128, 3C])
-//   P = softmax(S / sqrt(dk))   128 threads, thread t = TMEM lane t = query row t; fp32; exp2f with the
-//                               scale folded in; P written to smem as the bf16 K-major A operand
+//   P = softmax(S / sqrt(dk))   256 threads: thread t owns query row t % 128 (= TMEM lane) and the key half t / 128
+//                               (warps w and w + 4 read the same lane quarter); row max / sum of the two halves are
+//                               exchanged through smem; fp32; exp2f with the scale folded in; P written to smem as
+//                               the bf16 K-major A operand (each half writes its own 64-key chunk)
 //   O = P V        tcgen05.mma  128 x dk x 128   (B = V as loaded: [key][dk] = MN-major operand)
 //   out = O / rowsum  -> bf16, heads merged ([B*128, C])
 //
@@ -22,7 +24,7 @@ using namespace cft;
 using namespace cft::ptx;
 
 constexpr int kT = 128;          // tokens
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 
 constexpr int kMaxChunks = 4;
 struct AttnParams {
@@ -43,7 +45,7 @@ struct __align__(64) AttnMaps {
   CUtensorMap m[3];
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,6 +64,8 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
   uint64_t* tma_bar = bars;
   uint64_t* mma_bar = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 64);   // [max | sum][key half][row]
+  const int row = tid & (kT - 1), half = tid >> 7;
 
   if (tid == 0) {
     for (int c = 0; c < p.nchunk; ++c) prefetch_tmap(&maps.m[p.map[c]]);
@@ -110,39 +114,39 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
   mbar_wait(mma_bar, 0);
   tc_fence_after();
 
-  // ---- softmax: thread t owns row t (TMEM lane t) ----
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  // ---- softmax: thread (row, half) owns 64 of the 128 scores of its row; the scores stay in registers ----
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  uint32_t v0[32], v1[32];
+  tmem_ld32(tmem_s + lane_addr + static_cast<uint32_t>(64 * half), v0);
+  tmem_ld32(tmem_s + lane_addr + static_cast<uint32_t>(64 * half + 32), v1);
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < kT; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(tmem_s + lane_addr + c0, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-  }
+  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+  red[half * kT + row] = mx;
+  __syncthreads();
+  mx = fmaxf(red[row], red[kT + row]);
   const float mxs = mx * p.scale_log2e;
   float sum = 0.f;
-  for (int c0 = 0; c0 < kT; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(tmem_s + lane_addr + c0, v);
-    uint8_t* prow = sP + (c0 >> 6) * (kT * 128) + tid * 128;   // chunk of 64 keys, row = query
+  uint8_t* prow = sP + half * (kT * 128) + row * 128;           // chunk of 64 keys, row = query
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      float f[8];
+  for (int j = 0; j < 64; j += 8) {
+    float f[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float e = exp2f(fmaf(__uint_as_float(v[j + i]), p.scale_log2e, -mxs));
-        const __nv_bfloat16 eb = __float2bfloat16_rn(e);
-        f[i] = __bfloat162float(eb);
-        sum += f[i];                                            // normalise by what the MMA will see
-      }
-      const int ch = ((c0 & 63) + j) >> 3;                      // 16 B chunk within the 128 B row
-      *reinterpret_cast<bf16x8*>(prow + ((ch ^ (tid & 7)) << 4)) = pack8(f);
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t s = j < 32 ? v0[(j + i) & 31] : v1[(j + i) & 31];
+      const float e = exp2f(fmaf(__uint_as_float(s), p.scale_log2e, -mxs));
+      const __nv_bfloat16 eb = __float2bfloat16_rn(e);
+      f[i] = __bfloat162float(eb);
+      sum += f[i];                                              // normalise by what the MMA will see
     }
+    *reinterpret_cast<bf16x8*>(prow + (((j >> 3) ^ (row & 7)) << 4)) = pack8(f);   // 16 B chunk within the 128 B row
   }
+  red[2 * kT + half * kT + row] = sum;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  sum = red[2 * kT + row] + red[3 * kT + row];
 
   // ---- O = P V : A = P (K-major, SW128, two 64-key chunks), B = V (MN-major as loaded) ----
   if (tid == 0) {
@@ -166,10 +170,10 @@ cft_attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid
   mbar_wait(mma_bar, 1);
   tc_fence_after();
 
-  // ---- epilogue: out[b*128 + t][h*dk + c] = O[t][c] / sum ----
+  // ---- epilogue: out[b*128 + t][h*dk + c] = O[t][c] / sum; the two halves take alternate 32-column groups ----
   const float inv = 1.0f / sum;
-  __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * kT + tid) * p.C + h * p.dk;
-  for (int c0 = 0; c0 < p.dkp; c0 += 32) {
+  __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * kT + row) * p.C + h * p.dk;
+  for (int c0 = 32 * half; c0 < p.dkp; c0 += 64) {
     uint32_t v[32];
     tmem_ld32(tmem_o + lane_addr + c0, v);
 #pragma unroll
@@ -206,10 +210,10 @@ bool g_attr = false;
 int launch_attention(const AttnMaps& maps, const AttnParams& p, int B, cudaStream_t stream) {
   const int heads = p.heads;
   const int dk = p.dkp;
-  const int smem = 1024 + 3 * kT * dk * 2 + (dk >= 64 ? 0 : 2 * kT * 128) + 64;
+  const int smem = 1024 + 3 * kT * dk * 2 + (dk >= 64 ? 0 : 2 * kT * 128) + 64 + 4 * kT * 4;
   if (!g_attr) {
     int rc = check_cuda(cudaFuncSetAttribute(cft_attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             1024 + 3 * kT * 256 * 2 + 64),
+                                             1024 + 3 * kT * 256 * 2 + 64 + 4 * kT * 4),
                         "cudaFuncSetAttribute(attention_tcgen05)");
     if (rc) return rc;
     g_attr = true;
