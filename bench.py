@@ -16,11 +16,11 @@ Prints ONE JSON line on rank 0:
   roofline   the dominant kernel (tcgen05 implicit-GEMM conv/linear): the algorithmic FLOPs that kernel executes per
              step / time it is resident per step -- the union of the in-kernel %globaltimer spans of its launches
              inside a CUDA-graph replay (the timed mode), measured live -- against the measured sustained bf16 peak
-  cpu_baseline  the CPU oracle (a port of the reference's PyTorch forward) timed on the host cores on a
-             bounded sample (batch-1 forwards of the same graph/size)
---impl reference: the reference's own CPU implementation of the path (the oracle port; the reference is
-pure Python and /root/reference does not exist on the GPU box) on the host cores -- the fastest of 8/16/32/all threads,
-measured first -- rank 0 only.
+  cpu_baseline  the reference's forward on the host cores on a bounded sample (batch-1 forwards of the same graph / size):
+             the UNMODIFIED reference's own modules when its tree -- or the copy staged into baseline/_ref by
+             oracle/stage_reference.py, which travels to the GPU box -- is importable (kind "reference"), else the
+             oracle's restatement of it (kind "port")
+--impl reference: the same CPU forward as a whole arm (fastest of 8/16/32/all host threads, measured first) -- rank 0 only.
 """
 import argparse
 import importlib
@@ -148,23 +148,48 @@ def best_thread_count(fwd, candidates=None):
     return best_t
 
 
-def cpu_baseline(seconds_budget=20.0, batch=1):
-    """The oracle port of the reference forward on the host cores: batch-1 forwards of the headline graph."""
+def cpu_forward(batch):
+    """The reference's CPU forward of the headline graph on a seeded batch: (callable, kind, description).  `kind` is
+    "reference" when the UNMODIFIED reference's own modules run it (the tree, or its staged copy baseline/_ref --
+    oracle/stage_reference.py; fused and eval as test.py:66-68 / detect_twostream.py:40-41 run them, fp32 on the CPU),
+    else "port": the oracle's restatement of the same forward (oracle/cft_oracle.py)."""
     import torch
     from oracle import cft_oracle as O
+    from oracle import ref_shim
     pkg = importlib.import_module("multispectral-object-detection_b200")
     cfg = pkg.named_config(CFG_NAME)
-    sd = fused_state(O.init_state(cfg, seed=0), O.BN_EPS)       # BN folded, as the reference's inference path runs
     x, x2 = O.make_inputs(batch, H, W, seed=1)
-    best_thread_count(lambda: O.forward(sd, cfg, x, x2))      # also the warm-up
+    if ref_shim.available():
+        try:
+            yt = ref_shim.import_reference()
+            rm = yt.Model(ref_shim.reference_yaml(CFG_NAME), ch=3)
+            rm.load_state_dict(O.init_state(cfg, seed=0), strict=True)
+            rm = rm.float().fuse().eval()
+
+            def fwd_ref():
+                with torch.no_grad():
+                    return rm(x, x2)
+            fwd_ref()
+            return fwd_ref, "reference", "the reference's own modules (models/yolo_test.py Model, fused, eval), fp32, PyTorch CPU"
+        except Exception as e:       # an unimportable reference tree must not take the baseline down with it
+            sys.stderr.write(f"bench: reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port\n")
+    sd = fused_state(O.init_state(cfg, seed=0), O.BN_EPS)       # BN folded, as the reference's inference path runs
+    return (lambda: O.forward(sd, cfg, x, x2)), "port", "fp32 oracle port of the reference forward, PyTorch CPU"
+
+
+def cpu_baseline(seconds_budget=20.0, batch=1):
+    """The reference forward on the host cores (see cpu_forward): batch-1 forwards of the headline graph."""
+    import torch
+    fwd, kind, what = cpu_forward(batch)
+    best_thread_count(fwd)                                     # also the warm-up
     times, t_start = [], time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_start < seconds_budget and len(times) < 50):
         t0 = time.perf_counter()
-        O.forward(sd, cfg, x, x2)
+        fwd()
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": batch / med, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} forwards of batch {batch} @ {H}x{W} (fp32 oracle, median {med * 1e3:.0f} ms; "
+    return {"value": batch / med, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{len(times)} forwards of batch {batch} @ {H}x{W} ({what}, median {med * 1e3:.0f} ms; "
                       f"fastest of 8/16/32/{host_threads()} threads)"}
 
 
@@ -172,28 +197,23 @@ def run_reference(args, rank):
     if rank != 0:
         return
     import torch
-    from oracle import cft_oracle as O
-    pkg = importlib.import_module("multispectral-object-detection_b200")
-    cfg = pkg.named_config(CFG_NAME)
-    sd = fused_state(O.init_state(cfg, seed=0), O.BN_EPS)       # BN folded, as the reference's inference path runs
     b = 1                                             # bounded sample per step
-    x, x2 = O.make_inputs(b, H, W, seed=1)
-    best_thread_count(lambda: O.forward(sd, cfg, x, x2))      # fastest of 8/16/32/all host threads; doubles as warm-up
+    fwd, kind, what = cpu_forward(b)
+    best_thread_count(fwd)                            # fastest of 8/16/32/all host threads; doubles as warm-up
     for _ in range(max(0, min(args.warmup, 2) - 1)):
-        O.forward(sd, cfg, x, x2)
+        fwd()
     steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.forward(sd, cfg, x, x2)
+        fwd()
     dt = time.perf_counter() - t0
     v = b * steps / dt
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{CFG_NAME} forward, {H}x{W}, CPU oracle port of the reference forward, "
-                                   f"bounded sample: batch {b} per step"},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "config": {"workload": f"{CFG_NAME} forward, {H}x{W}, {what}, bounded sample: batch {b} per step"},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
                              "sample": f"{steps} forwards of batch {b} @ {H}x{W}"},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
