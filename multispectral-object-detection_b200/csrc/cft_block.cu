@@ -850,7 +850,6 @@ bool make_plan(int B, int d, int heads, int forced_c, Plan* pl) {
 
 bool g_attr_set = false;
 unsigned long long* g_trace = nullptr;   // cft_debug_block_trace
-const int g_force_c = getenv("CFT_BLOCK_CLUSTER") ? atoi(getenv("CFT_BLOCK_CLUSTER")) : 0;
 
 template <int DC, int HP>
 cudaError_t launch_block(const cudaLaunchConfig_t& cfg, const BlockMaps& maps, const BlockParams& p) {
@@ -875,7 +874,7 @@ extern "C" long long cft_gpt_block_workspace_bytes(int B, int d) {
 
 extern "C" int cft_gpt_block_supported(int B, int d, int heads, int tokens) {
   Plan pl;
-  return (tokens == kT && B > 0 && make_plan(B, d, heads, g_force_c, &pl)) ? 1 : 0;
+  return (tokens == kT && B > 0 && make_plan(B, d, heads, 0, &pl)) ? 1 : 0;
 }
 
 extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
@@ -886,7 +885,7 @@ extern "C" int cft_gpt_block(const cft_gpt_block_args* a, void* stream_v) {
               "cft_gpt_block: null pointer");
   CFT_REQUIRE(a->B > 0 && a->layers > 0 && a->tokens == kT, "cft_gpt_block: need B > 0, layers > 0, 128 tokens per image");
   Plan pl;
-  if (!make_plan(a->B, a->d, a->heads, a->cluster > 0 ? a->cluster : g_force_c, &pl)) {
+  if (!make_plan(a->B, a->d, a->heads, a->cluster > 0 ? a->cluster : 0, &pl)) {
     set_error("cft_gpt_block: shape outside the fused kernel (d %d heads %d cluster %d): use the per-op path", a->d,
               a->heads, a->cluster);
     return CFT_E_UNSUPPORTED;
