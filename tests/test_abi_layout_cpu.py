@@ -87,3 +87,26 @@ def test_ctypes_signatures_match_the_header_prototypes(cft):
         want_ret = {"int": C.c_int, "long long": C.c_longlong, "const char*": C.c_char_p}[ret]
         assert restype is want_ret, (name, ret, restype)
     assert names == set(L.SIGNATURES), sorted(set(L.SIGNATURES) ^ names)
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not available")
+def test_enum_constants_match_the_header(cft, tmp_path):
+    L = cft._lib
+    kid = {"conv_tcgen05": "CFT_K_CONV_TCGEN05", "conv_ref": "CFT_K_CONV_REF", "focus": "CFT_K_FOCUS", "maxpool": "CFT_K_MAXPOOL",
+           "upsample": "CFT_K_UPSAMPLE", "add": "CFT_K_ADD", "copy": "CFT_K_COPY", "pool_tokens": "CFT_K_POOL_TOKENS",
+           "layernorm": "CFT_K_LAYERNORM", "attention": "CFT_K_ATTENTION", "unpool": "CFT_K_UNPOOL", "detect": "CFT_K_DETECT",
+           "nms": "CFT_K_NMS", "gpt_block": "CFT_K_GPT_BLOCK"}
+    assert set(kid) == set(L.KERNEL_IDS)
+    consts = {"CFT_ACT_NONE": L.ACT_NONE, "CFT_ACT_SILU": L.ACT_SILU, "CFT_ACT_GELU": L.ACT_GELU, "CFT_DT_BF16": L.DT_BF16,
+              "CFT_DT_F32": L.DT_F32, "CFT_DT_U8": L.DT_U8, "CFT_K_COUNT": len(L.KERNEL_IDS)}
+    consts.update({c: L.KERNEL_IDS[k] for k, c in kid.items()})
+    body = "\n".join(f'  printf("{c} %d\\n", (int){c});' for c in list(consts) + ["CFT_ABI_VERSION"])
+    src = tmp_path / "enums.c"
+    src.write_text('#include <stdio.h>\n#include "cft_b200.h"\nint main(void) {\n' + body + "\n  return 0;\n}\n")
+    exe = tmp_path / "enums"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for c, v in consts.items():
+        assert int(got[c]) == v, (c, got[c], v)
+    assert int(got["CFT_ABI_VERSION"]) == cft.load().cft_abi_version()        # the built library is of this header
